@@ -1,0 +1,41 @@
+"""Build the CUDA engine in-tree: spacegym_b200/libspacegym_b200.so (sm_100a only).
+
+    python -m spacegym_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the tree.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = [os.path.join(HERE, "csrc", f) for f in ("sg_engine.cu", "sg_device.cuh")] + [
+    os.path.join(ROOT, "include", "spacegym_b200.h")]
+OUT = os.path.join(HERE, "libspacegym_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(s) > t for s in SRC)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC[0], "-o", OUT + ".tmp"]
+    subprocess.check_call(cmd)
+    os.replace(OUT + ".tmp", OUT)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

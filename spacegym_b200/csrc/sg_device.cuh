@@ -1,0 +1,902 @@
+// sg_device.cuh — device-side physics, integrator, rewards, observation and resets of the
+// B200-native Space-Gym engine.  One CUDA thread owns one environment; everything here
+// works on registers.  FP64 throughout, except the float32 roundings the reference
+// inherits from NumPy-2 scalar promotion, which are reproduced with
+// non-contractable __f*_rn intrinsics.
+//
+// Reference behaviour followed (MIMUW-RL/space-gym tree, SciPy 1.18.1 = `scipy:`):
+//   RHS / forces          gym_space/dynamic_model.py:129-176, gym_space/helpers.py:22-35
+//   events                gym_space/dynamic_model.py:183-217
+//   RK45 + controller     scipy:rk.py:14-71,85-176,538-565; scipy:common.py:68-134
+//   event loop, roots     scipy:ivp.py:52-157,651-699; scipy.optimize brentq (Brent 1973)
+//   dense output          scipy:rk.py:178-180,715-737
+//   observation           gym_space/envs/spaceship_env.py:113-140, kepler.py:172-187
+//   rewards               gym_space/envs/goal.py:147-165,204-227; kepler.py:43-156
+//   resets                gym_space/envs/goal.py:133-145, hexagonal_tiling.py:53-158, kepler.py:233-267
+//
+// The arithmetic is NOT a transcription: the ODE is integrated in Nystrom form (the force
+// does not depend on velocity, the heading is a known polynomial in time), gravity uses
+// rsqrt, lidars and the Kepler geometry are trig-free.  Control flow (accept/reject,
+// step-size selection, event detection, earliest root) follows SciPy decision by decision.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+namespace sg {
+
+constexpr double kG = 6.6743e-11;  // helpers.py:19
+constexpr double kPi = 3.141592653589793;
+constexpr double kTwoPi = 2 * 3.141592653589793;
+constexpr double kRtol = 1e-3, kAtol = 1e-6;  // solve_ivp defaults
+constexpr double kEps = 2.220446049250313e-16;
+constexpr double kInvSqrt6 = 0.40824829046386301637;
+
+enum { TASK_GOAL = 0, TASK_KEPLER = 1 };
+enum { STEER_ACC = 0, STEER_VEL = 1 };
+
+// ---- Dormand-Prince tableau (scipy:rk.py:538-565), 1-based stage names ------------------
+constexpr double a21 = 1.0 / 5;
+constexpr double a31 = 3.0 / 40, a32 = 9.0 / 40;
+constexpr double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
+constexpr double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
+constexpr double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176,
+                 a65 = -5103.0 / 18656;
+constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+constexpr double e1 = -71.0 / 57600, e3 = 71.0 / 16695, e4 = -71.0 / 1920, e5 = 17253.0 / 339200,
+                 e6 = -22.0 / 525, e7 = 1.0 / 40;
+constexpr double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
+
+// Nystrom coefficients: position stage i = x0 + c_i h v0 + h^2 sum_k ab_ik A_k, with
+// ab_ik = sum_j a_ij a_jk (the stage velocities are eliminated).
+constexpr double ab31 = a32 * a21;
+constexpr double ab41 = a42 * a21 + a43 * a31, ab42 = a43 * a32;
+constexpr double ab51 = a52 * a21 + a53 * a31 + a54 * a41, ab52 = a53 * a32 + a54 * a42, ab53 = a54 * a43;
+constexpr double ab61 = a62 * a21 + a63 * a31 + a64 * a41 + a65 * a51,
+                 ab62 = a63 * a32 + a64 * a42 + a65 * a52, ab63 = a64 * a43 + a65 * a53, ab64 = a65 * a54;
+constexpr double bb1 = b3 * a31 + b4 * a41 + b5 * a51 + b6 * a61, bb2 = b3 * a32 + b4 * a42 + b5 * a52 + b6 * a62,
+                 bb3 = b4 * a43 + b5 * a53 + b6 * a63, bb4 = b5 * a54 + b6 * a64, bb5 = b6 * a65;
+// error estimate of the position rows: h^2 sum_k eb_k A_k
+constexpr double eb1 = e3 * a31 + e4 * a41 + e5 * a51 + e6 * a61 + e7 * b1,
+                 eb2 = e3 * a32 + e4 * a42 + e5 * a52 + e6 * a62, eb3 = e4 * a43 + e5 * a53 + e6 * a63 + e7 * b3,
+                 eb4 = e5 * a54 + e6 * a64 + e7 * b4, eb5 = e6 * a65 + e7 * b5, eb6 = e7 * b6;
+// heading: theta_i = theta0 + c_i h omega0 + h^2 alpha cs_i, cs_i = sum_j a_ij c_j
+constexpr double cs3 = a32 * c2, cs4 = a42 * c2 + a43 * c3, cs5 = a52 * c2 + a53 * c3 + a54 * c4,
+                 cs6 = a62 * c2 + a63 * c3 + a64 * c4 + a65 * c5, cs7 = b3 * c3 + b4 * c4 + b5 * c5 + b6 * 1.0;
+
+// dense-output matrix P (scipy:rk.py:554-565), rows = stages 1..7 (row 2 is zero)
+constexpr double P11 = 1, P12 = -8048581381.0 / 2820520608.0, P13 = 8663915743.0 / 2820520608.0,
+                 P14 = -12715105075.0 / 11282082432.0;
+constexpr double P32 = 131558114200.0 / 32700410799.0, P33 = -68118460800.0 / 10900136933.0,
+                 P34 = 87487479700.0 / 32700410799.0;
+constexpr double P42 = -1754552775.0 / 470086768.0, P43 = 14199869525.0 / 1410260304.0,
+                 P44 = -10690763975.0 / 1880347072.0;
+constexpr double P52 = 127303824393.0 / 49829197408.0, P53 = -318862633887.0 / 49829197408.0,
+                 P54 = 701980252875.0 / 199316789632.0;
+constexpr double P62 = -282668133.0 / 205662961.0, P63 = 2019193451.0 / 616988883.0,
+                 P64 = -1453857185.0 / 822651844.0;
+constexpr double P72 = 40617522.0 / 29380423.0, P73 = -110615467.0 / 29380423.0, P74 = 69997945.0 / 29380423.0;
+
+// ---- engine constants, passed to kernels by value ------------------------------------------
+struct DevCfg {
+    // struct-of-arrays state (include/spacegym_b200.h: sg_layout)
+    double* ship;
+    double* planets;
+    double* goal;
+    double* orbit;
+    double* col_shift;
+    double* ep_return;
+    unsigned long long* free_tiles;
+    uint32_t* tile_word;
+    uint32_t* elapsed;
+    uint32_t* rng_ctr;
+    uint32_t* status;
+    double* stats;  // 4 doubles: sum return, sum length, episodes, goals
+    long long n;
+    long long first_env;
+    unsigned long long seed;
+    int max_episode_steps, randomize, auto_reset, rows, cols;
+    // physics
+    double T, half_ws, two_over_ws, om_max, inv_mass, moi;
+    double max_engine, max_thruster;          // float64 action path (discrete)
+    float max_engine_f32, max_thruster_f32;   // float32 action path (continuous)
+    double gm0;                               // G * m_ship * M_planet (all Goal planets equal)
+    double r0, r1;                            // event radii: Goal planets r0; Kepler planet r0, border r1
+    // Goal reward
+    double survival, goal_vel, safety, sparse, danger_zone, goal_radius, ship_radius;
+    // hexagonal tiling
+    double ws, hex_a, hex_height, hex_width, free_x;
+    // Kepler
+    double orbit_a, numC, radC, actC;
+    float actC_f32;
+    double kep_lo, kep_hi;  // reset radius range (kepler.py:235-237)
+};
+
+// ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) ---------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// Draw session on an env's stream 0: counter = (env_lo, env_hi, block, 0); one block = 2 doubles.
+struct Rng {
+    uint32_t k0, k1, e0, e1, ctr;
+    double ubuf, nbuf;
+    bool have_u, have_n;
+    __device__ __forceinline__ void open(unsigned long long seed, unsigned long long env, uint32_t ctr_) {
+        k0 = (uint32_t)seed;
+        k1 = (uint32_t)(seed >> 32);
+        e0 = (uint32_t)env;
+        e1 = (uint32_t)(env >> 32);
+        ctr = ctr_;
+        have_u = have_n = false;
+    }
+    __device__ __forceinline__ void fresh_block() { have_u = have_n = false; }
+    __device__ double uniform() {
+        if (have_u) {
+            have_u = false;
+            return ubuf;
+        }
+        uint32_t o[4];
+        philox4x32_10(e0, e1, ctr, 0u, k0, k1, o);
+        ctr += 1;
+        unsigned long long a = ((unsigned long long)o[1] << 32) | o[0];
+        unsigned long long b = ((unsigned long long)o[3] << 32) | o[2];
+        ubuf = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+        have_u = true;
+        return (double)(a >> 11) * (1.0 / 9007199254740992.0);
+    }
+    __device__ double normal() {  // Box-Muller
+        if (have_n) {
+            have_n = false;
+            return nbuf;
+        }
+        double u1 = 1.0 - uniform();
+        double u2 = uniform();
+        double r = sqrt(-2.0 * log(u1));
+        double s, c;
+        sincos(kTwoPi * u2, &s, &c);
+        nbuf = r * s;
+        have_n = true;
+        return r * c;
+    }
+};
+
+// synthetic actions: counter = (env_lo, env_hi, step_lo, 0x80000000 | step_hi)
+__device__ __forceinline__ void random_action(unsigned long long seed, unsigned long long env,
+                                              unsigned long long step, bool discrete, float& a0, float& a1) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)step,
+                  0x80000000u | (uint32_t)((step >> 32) & 0x7fffffffu), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    if (discrete) {
+        a0 = (float)(uint32_t)(((unsigned long long)o[0] * 6u) >> 32);
+        a1 = 0.0f;
+    } else {
+        a0 = __fsub_rn(__fmul_rn((float)(o[0] >> 8), 1.0f / 8388608.0f), 1.0f);
+        a1 = __fsub_rn(__fmul_rn((float)(o[1] >> 8), 1.0f / 8388608.0f), 1.0f);
+    }
+}
+
+// ---- per-thread environment registers --------------------------------------------------------
+template <int TASK_, int NP_, int STEER_, int DISC_>
+struct Traits {
+    static constexpr int TASK = TASK_;
+    static constexpr int NP = NP_;                                   // Goal: planets; Kepler: 1 gravitating body
+    static constexpr int STEER = STEER_;
+    static constexpr int DISC = DISC_;
+    static constexpr int NEV = (TASK_ == TASK_GOAL ? NP_ : 2) + 3;   // events (dynamic_model.py:183-217)
+    static constexpr int D = TASK_ == TASK_GOAL ? 9 + 2 * NP_ : 10;  // observation length
+};
+
+template <class TR>
+struct EnvRegs {
+    double x, y, th, vx, vy, om;
+    double px[TR::NP], py[TR::NP];  // planet centres (Kepler: the origin)
+    double gx, gy;                  // goal (Goal)
+    double ecc, ang;                // reference orbit (Kepler)
+};
+
+// translated action (spaceship_env.py:189-214) folded with the force scales (dynamic_model.py:140,171,175)
+struct Act {
+    double fs;        // engine force magnitude
+    double w;         // velocity steering: heading rate
+    double alpha;     // acceleration steering: angular acceleration
+    double act_term;  // Kepler: act_penalty_C * ||action|| in the reference's dtype
+};
+
+template <class TR>
+__device__ __forceinline__ Act translate_action(const DevCfg& c, float r0, float r1) {
+    Act a;
+    if (TR::DISC) {
+        // DiscreteSpaceshipEnv._translate_raw_action: python floats -> float64 everywhere
+        int k = (int)r0;
+        double e = (k == 1 || k >= 4) ? 1.0 : 0.0;
+        double t = (k == 2 || k == 4) ? -1.0 : ((k == 3 || k == 5) ? 1.0 : 0.0);
+        a.fs = e * c.max_engine;
+        a.w = t * 5.0;
+        a.alpha = (t * c.max_thruster) / c.moi;
+        a.act_term = c.actC * sqrt(e * e + t * t);
+    } else {
+        // float32 arithmetic, never contracted (NEP-50 promotion in the reference)
+        float e32 = __fdiv_rn(__fadd_rn(r0, 1.0f), 2.0f);
+        float t32 = r1;
+        a.fs = (double)__fmul_rn(e32, c.max_engine_f32);
+        a.w = (double)__fmul_rn(t32, 5.0f);
+        a.alpha = (double)__fmul_rn(t32, c.max_thruster_f32) / c.moi;
+        float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(e32, e32), __fmul_rn(t32, t32)));
+        a.act_term = (double)__fmul_rn(c.actC_f32, nrm);
+    }
+    return a;
+}
+
+// ---- forces (dynamic_model.py:145-176, helpers.py:22-35) -----------------------------------------
+// a = (-(cos th, sin th) fs + sum_p GM d_p / |d_p|^3) / m.  The Kepler border has mass 0 and
+// contributes exactly 0, so it is not a gravitating body here.
+template <class TR>
+__device__ __forceinline__ void accel(const DevCfg& c, const EnvRegs<TR>& e, double x, double y, double cth,
+                                      double sth, double fs, double& ax, double& ay) {
+    double fx = -cth * fs, fy = -sth * fs;
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        double dx = e.px[p] - x, dy = e.py[p] - y;
+        double inv = rsqrt(dx * dx + dy * dy);
+        double s = c.gm0 * (inv * inv * inv);
+        fx = fma(dx, s, fx);
+        fy = fma(dy, s, fy);
+    }
+    ax = fx * c.inv_mass;
+    ay = fy * c.inv_mass;
+}
+
+// ---- termination events (dynamic_model.py:183-217) -------------------------------------------------
+// order: planets..., world_max, world_min, angular velocity.  pd = planet-centre distances.
+template <class TR>
+__device__ __forceinline__ void event_values(const DevCfg& c, const EnvRegs<TR>& e, double x, double y, double om,
+                                             double (&g)[TR::NEV], double (&pd)[TR::NP]) {
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        double dx = e.px[p] - x, dy = e.py[p] - y;
+        pd[p] = sqrt(dx * dx + dy * dy);
+    }
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int p = 0; p < TR::NP; ++p) g[p] = pd[p] - c.r0;
+    } else {
+        g[0] = pd[0] - c.r0;
+        g[1] = pd[0] - c.r1;
+    }
+    g[TR::NEV - 3] = fmin(c.half_ws - x, c.half_ws - y);
+    g[TR::NEV - 2] = fmin(c.half_ws + x, c.half_ws + y);
+    g[TR::NEV - 1] = c.om_max - fabs(om);
+}
+
+// ---- cold path: dense output + Brent roots of the active events -------------------------------------
+template <class TR>
+struct EventIO {
+    // in: state at the start of the accepted step, the step, its seven force evaluations
+    double x, y, th, vx, vy, om, alpha;
+    double h, t_old;
+    double Ax[7], Ay[7];
+    double px[TR::NP], py[TR::NP];
+    uint32_t active;
+    // out
+    double t_root;
+    uint32_t status;
+};
+
+template <class TR>
+struct Dense {  // scipy:rk.py:715-737, specialised: heading and its rate are exact polynomials
+    double x0, y0, th0, vx0, vy0, om0, alpha, h, t_old;
+    double Qx[4], Qy[4], Qvx[4], Qvy[4];
+    __device__ void eval(double t, double& x, double& y, double& th, double& vx, double& vy, double& om) const {
+        double s = (t - t_old) / h;
+        double s2 = s * s, s3 = s2 * s, s4 = s3 * s;
+        x = x0 + h * (Qx[0] * s + Qx[1] * s2 + Qx[2] * s3 + Qx[3] * s4);
+        y = y0 + h * (Qy[0] * s + Qy[1] * s2 + Qy[2] * s3 + Qy[3] * s4);
+        vx = vx0 + h * (Qvx[0] * s + Qvx[1] * s2 + Qvx[2] * s3 + Qvx[3] * s4);
+        vy = vy0 + h * (Qvy[0] * s + Qvy[1] * s2 + Qvy[2] * s3 + Qvy[3] * s4);
+        double dt = t - t_old;
+        om = om0 + alpha * dt;
+        th = th0 + om0 * dt + 0.5 * alpha * dt * dt;
+    }
+};
+
+template <class TR>
+__device__ double event_at(const DevCfg& c, const EventIO<TR>& io, const Dense<TR>& d, int ev, double t) {
+    double x, y, th, vx, vy, om;
+    d.eval(t, x, y, th, vx, vy, om);
+    constexpr int NPL = TR::NEV - 3;  // planet-type events
+    if (ev < NPL) {
+        int p = (TR::TASK == TASK_GOAL) ? ev : 0;
+        double dx = io.px[p] - x, dy = io.py[p] - y;
+        double r = (TR::TASK == TASK_GOAL) ? c.r0 : (ev == 0 ? c.r0 : c.r1);
+        return sqrt(dx * dx + dy * dy) - r;
+    }
+    if (ev == NPL) return fmin(c.half_ws - x, c.half_ws - y);
+    if (ev == NPL + 1) return fmin(c.half_ws + x, c.half_ws + y);
+    return c.om_max - fabs(om);
+}
+
+// Brent's method as scipy.optimize.brentq runs it from scipy:ivp.py:52-77 (xtol = rtol = 4 eps,
+// 100 iterations): bisection guarded secant / inverse quadratic interpolation.
+template <class TR>
+__device__ double brent_root(const DevCfg& c, const EventIO<TR>& io, const Dense<TR>& d, int ev, double xa,
+                             double xb, uint32_t& status) {
+    const double tol = 4 * kEps;
+    double xpre = xa, xcur = xb, xblk = 0, fblk = 0, spre = 0, scur = 0;
+    double fpre = event_at(c, io, d, ev, xpre), fcur = event_at(c, io, d, ev, xcur);
+    if (fpre == 0) return xpre;
+    if (fcur == 0) return xcur;
+    if (signbit(fpre) == signbit(fcur)) {
+        status |= 2u;  // SG_ENV_BRENT_SIGN: the reference would raise here
+        return xb;
+    }
+    for (int it = 0; it < 100; ++it) {
+        if (fpre != 0 && fcur != 0 && (signbit(fpre) != signbit(fcur))) {
+            xblk = xpre;
+            fblk = fpre;
+            spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur;
+            xcur = xblk;
+            xblk = xpre;
+            fpre = fcur;
+            fcur = fblk;
+            fblk = fpre;
+        }
+        double delta = (tol + tol * fabs(xcur)) / 2;
+        double sbis = (xblk - xcur) / 2;
+        if (fcur == 0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            double stry;
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);
+            } else {
+                double dpre = (fpre - fcur) / (xpre - xcur);
+                double dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            if (2 * fabs(stry) < fmin(fabs(spre), 3 * fabs(sbis) - delta)) {
+                spre = scur;
+                scur = stry;
+            } else {
+                spre = sbis;
+                scur = sbis;
+            }
+        } else {
+            spre = sbis;
+            scur = sbis;
+        }
+        xpre = xcur;
+        fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        fcur = event_at(c, io, d, ev, xcur);
+    }
+    return xcur;
+}
+
+// scipy:ivp.py:683-697: roots of all active events, earliest one terminates; state := sol(t*)
+template <class TR>
+__device__ __noinline__ void handle_events(const DevCfg& c, EventIO<TR>* io) {
+    Dense<TR> d;
+    d.x0 = io->x; d.y0 = io->y; d.th0 = io->th; d.vx0 = io->vx; d.vy0 = io->vy; d.om0 = io->om;
+    d.alpha = io->alpha; d.h = io->h; d.t_old = io->t_old;
+    const double h = io->h;
+    const double* Ax = io->Ax;
+    const double* Ay = io->Ay;
+    // stage velocities (rows 0-1 of K): V_i = v + h sum_j a_ij A_j
+    double Vx[7], Vy[7];
+    Vx[0] = io->vx; Vy[0] = io->vy;
+    Vx[1] = io->vx + h * (a21 * Ax[0]);
+    Vy[1] = io->vy + h * (a21 * Ay[0]);
+    Vx[2] = io->vx + h * (a31 * Ax[0] + a32 * Ax[1]);
+    Vy[2] = io->vy + h * (a31 * Ay[0] + a32 * Ay[1]);
+    Vx[3] = io->vx + h * (a41 * Ax[0] + a42 * Ax[1] + a43 * Ax[2]);
+    Vy[3] = io->vy + h * (a41 * Ay[0] + a42 * Ay[1] + a43 * Ay[2]);
+    Vx[4] = io->vx + h * (a51 * Ax[0] + a52 * Ax[1] + a53 * Ax[2] + a54 * Ax[3]);
+    Vy[4] = io->vy + h * (a51 * Ay[0] + a52 * Ay[1] + a53 * Ay[2] + a54 * Ay[3]);
+    Vx[5] = io->vx + h * (a61 * Ax[0] + a62 * Ax[1] + a63 * Ax[2] + a64 * Ax[3] + a65 * Ax[4]);
+    Vy[5] = io->vy + h * (a61 * Ay[0] + a62 * Ay[1] + a63 * Ay[2] + a64 * Ay[3] + a65 * Ay[4]);
+    Vx[6] = io->vx + h * (b1 * Ax[0] + b3 * Ax[2] + b4 * Ax[3] + b5 * Ax[4] + b6 * Ax[5]);
+    Vy[6] = io->vy + h * (b1 * Ay[0] + b3 * Ay[2] + b4 * Ay[3] + b5 * Ay[4] + b6 * Ay[5]);
+    const double Pm[7][4] = {{P11, P12, P13, P14}, {0, 0, 0, 0},       {0, P32, P33, P34}, {0, P42, P43, P44},
+                             {0, P52, P53, P54},   {0, P62, P63, P64}, {0, P72, P73, P74}};
+    for (int j = 0; j < 4; ++j) {
+        double qx = 0, qy = 0, qvx = 0, qvy = 0;
+        for (int k = 0; k < 7; ++k) {
+            qx += Vx[k] * Pm[k][j];
+            qy += Vy[k] * Pm[k][j];
+            qvx += Ax[k] * Pm[k][j];
+            qvy += Ay[k] * Pm[k][j];
+        }
+        d.Qx[j] = qx; d.Qy[j] = qy; d.Qvx[j] = qvx; d.Qvy[j] = qvy;
+    }
+    double best = INFINITY;
+    uint32_t status = 0;
+    for (int ev = 0; ev < TR::NEV; ++ev) {
+        if (!((io->active >> ev) & 1u)) continue;
+        double root = brent_root(c, *io, d, ev, io->t_old, io->t_old + io->h, status);
+        if (root < best) best = root;
+    }
+    io->t_root = best;
+    io->status = status;
+    d.eval(best, io->x, io->y, io->th, io->vx, io->vy, io->om);
+}
+
+// ---- one env.step of the physics: solve_ivp(RK45, (0, T), events) -----------------------------------
+// Returns done.  On exit e holds the new state (heading wrapped) and pd the planet distances there.
+template <class TR>
+__device__ __forceinline__ bool make_step(const DevCfg& c, EnvRegs<TR>& e, const Act& act, uint32_t& status,
+                                          double (&pd)[TR::NP]) {
+    constexpr int NEV = TR::NEV;
+    const double T = c.T;
+    const double alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
+    if (TR::STEER == STEER_VEL) e.om = act.w;  // the RHS overwrites omega in place (quirk 1)
+    double x = e.x, y = e.y, th = e.th, vx = e.vx, vy = e.vy, om = e.om;
+    const double fs = act.fs;
+
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    double A1x, A1y;
+    accel(c, e, x, y, cs, sn, fs, A1x, A1y);  // f0
+
+    // select_initial_step (scipy:common.py:109-134), error_estimator_order = 4
+    double h_abs;
+    {
+        double rx = 1.0 / (kAtol + fabs(x) * kRtol), ry = 1.0 / (kAtol + fabs(y) * kRtol);
+        double rth = 1.0 / (kAtol + fabs(th) * kRtol), rvx = 1.0 / (kAtol + fabs(vx) * kRtol);
+        double rvy = 1.0 / (kAtol + fabs(vy) * kRtol), rom = 1.0 / (kAtol + fabs(om) * kRtol);
+        double q;
+        double S0 = 0, S1 = 0, S2 = 0;
+        q = x * rx; S0 = fma(q, q, S0);
+        q = y * ry; S0 = fma(q, q, S0);
+        q = th * rth; S0 = fma(q, q, S0);
+        q = vx * rvx; S0 = fma(q, q, S0);
+        q = vy * rvy; S0 = fma(q, q, S0);
+        q = om * rom; S0 = fma(q, q, S0);
+        q = vx * rx; S1 = fma(q, q, S1);
+        q = vy * ry; S1 = fma(q, q, S1);
+        q = om * rth; S1 = fma(q, q, S1);
+        q = A1x * rvx; S1 = fma(q, q, S1);
+        q = A1y * rvy; S1 = fma(q, q, S1);
+        q = alpha * rom; S1 = fma(q, q, S1);
+        double d0 = sqrt(S0) * kInvSqrt6, d1 = sqrt(S1) * kInvSqrt6;
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, T);
+        double s1, c1, Bx, By;
+        sincos(th + h0 * om, &s1, &c1);
+        accel(c, e, x + h0 * vx, y + h0 * vy, c1, s1, fs, Bx, By);  // f(y0 + h0 f0)
+        q = h0 * A1x * rx; S2 = fma(q, q, S2);
+        q = h0 * A1y * ry; S2 = fma(q, q, S2);
+        q = h0 * alpha * rth; S2 = fma(q, q, S2);
+        q = (Bx - A1x) * rvx; S2 = fma(q, q, S2);
+        q = (By - A1y) * rvy; S2 = fma(q, q, S2);
+        double d2 = sqrt(S2) * kInvSqrt6 / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / fmax(d1, d2), 0.2);
+        h_abs = fmin(fmin(100 * h0, h1), T);
+    }
+
+    double g[NEV];
+    event_values(c, e, x, y, om, g, pd);  // scipy:ivp.py:651 (after the omega overwrite)
+
+    double t = 0.0;
+    bool done = false;
+    for (;;) {
+        // RungeKutta._step_impl (scipy:rk.py:111-176)
+        double min_step = 10 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false, failed = false;
+        double h, t_new, xn, yn, vxn, vyn, thn, omn;
+        double A2x, A2y, A3x, A3y, A4x, A4y, A5x, A5y, A6x, A6y, A7x, A7y;
+        for (;;) {
+            if (h_abs < min_step) {
+                failed = true;
+                break;
+            }
+            t_new = t + h_abs;
+            if (t_new - T > 0) t_new = T;
+            h = t_new - t;
+            h_abs = fabs(h);
+            const double hh = h * h, hv = h, ha = hh * alpha;
+            // rk_step (scipy:rk.py:14-71) in Nystrom form
+            sincos(th + (c2 * hv) * om, &sn, &cs);
+            accel(c, e, x + (c2 * hv) * vx, y + (c2 * hv) * vy, cs, sn, fs, A2x, A2y);
+            sincos(th + (c3 * hv) * om + cs3 * ha, &sn, &cs);
+            accel(c, e, x + (c3 * hv) * vx + hh * (ab31 * A1x), y + (c3 * hv) * vy + hh * (ab31 * A1y), cs, sn, fs, A3x,
+                  A3y);
+            sincos(th + (c4 * hv) * om + cs4 * ha, &sn, &cs);
+            accel(c, e, x + (c4 * hv) * vx + hh * (ab41 * A1x + ab42 * A2x),
+                  y + (c4 * hv) * vy + hh * (ab41 * A1y + ab42 * A2y), cs, sn, fs, A4x, A4y);
+            sincos(th + (c5 * hv) * om + cs5 * ha, &sn, &cs);
+            accel(c, e, x + (c5 * hv) * vx + hh * (ab51 * A1x + ab52 * A2x + ab53 * A3x),
+                  y + (c5 * hv) * vy + hh * (ab51 * A1y + ab52 * A2y + ab53 * A3y), cs, sn, fs, A5x, A5y);
+            sincos(th + hv * om + cs6 * ha, &sn, &cs);
+            accel(c, e, x + hv * vx + hh * (ab61 * A1x + ab62 * A2x + ab63 * A3x + ab64 * A4x),
+                  y + hv * vy + hh * (ab61 * A1y + ab62 * A2y + ab63 * A3y + ab64 * A4y), cs, sn, fs, A6x, A6y);
+            xn = x + hv * vx + hh * (bb1 * A1x + bb2 * A2x + bb3 * A3x + bb4 * A4x + bb5 * A5x);
+            yn = y + hv * vy + hh * (bb1 * A1y + bb2 * A2y + bb3 * A3y + bb4 * A4y + bb5 * A5y);
+            vxn = vx + h * (b1 * A1x + b3 * A3x + b4 * A4x + b5 * A5x + b6 * A6x);
+            vyn = vy + h * (b1 * A1y + b3 * A3y + b4 * A4y + b5 * A5y + b6 * A6y);
+            thn = th + hv * om + cs7 * ha;
+            omn = om + h * alpha;
+            sincos(thn, &sn, &cs);
+            accel(c, e, xn, yn, cs, sn, fs, A7x, A7y);  // f_new (FSAL)
+            // error norm (scipy:rk.py:105-109,141-143); the heading rows are exactly integrable -> 0
+            double ex = hh * (eb1 * A1x + eb2 * A2x + eb3 * A3x + eb4 * A4x + eb5 * A5x + eb6 * A6x);
+            double ey = hh * (eb1 * A1y + eb2 * A2y + eb3 * A3y + eb4 * A4y + eb5 * A5y + eb6 * A6y);
+            double evx = h * (e1 * A1x + e3 * A3x + e4 * A4x + e5 * A5x + e6 * A6x + e7 * A7x);
+            double evy = h * (e1 * A1y + e3 * A3y + e4 * A4y + e5 * A5y + e6 * A6y + e7 * A7y);
+            ex /= kAtol + fmax(fabs(x), fabs(xn)) * kRtol;
+            ey /= kAtol + fmax(fabs(y), fabs(yn)) * kRtol;
+            evx /= kAtol + fmax(fabs(vx), fabs(vxn)) * kRtol;
+            evy /= kAtol + fmax(fabs(vy), fabs(vyn)) * kRtol;
+            double err = sqrt(ex * ex + ey * ey + evx * evx + evy * evy) * kInvSqrt6;
+            if (err < 1) {
+                if (t_new < T) {  // the next step size only matters if another step follows
+                    double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+                    if (rejected) factor = fmin(1.0, factor);
+                    h_abs *= factor;
+                }
+                break;
+            }
+            h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+            rejected = true;
+        }
+        if (failed) {
+            status |= 1u;  // SG_ENV_STEP_TOO_SMALL
+            break;
+        }
+        // events at the accepted end point (scipy:ivp.py:679-699)
+        double gn[NEV];
+        event_values(c, e, xn, yn, omn, gn, pd);
+        uint32_t active = 0;
+#pragma unroll
+        for (int i = 0; i < NEV; ++i) {
+            bool up = (g[i] <= 0) && (gn[i] >= 0);
+            bool down = (g[i] >= 0) && (gn[i] <= 0);
+            if (up || down) active |= (1u << i);
+        }
+        if (active) {
+            EventIO<TR> io;
+            io.x = x; io.y = y; io.th = th; io.vx = vx; io.vy = vy; io.om = om; io.alpha = alpha;
+            io.h = h; io.t_old = t;
+            io.Ax[0] = A1x; io.Ax[1] = A2x; io.Ax[2] = A3x; io.Ax[3] = A4x; io.Ax[4] = A5x; io.Ax[5] = A6x; io.Ax[6] = A7x;
+            io.Ay[0] = A1y; io.Ay[1] = A2y; io.Ay[2] = A3y; io.Ay[3] = A4y; io.Ay[4] = A5y; io.Ay[5] = A6y; io.Ay[6] = A7y;
+#pragma unroll
+            for (int p = 0; p < TR::NP; ++p) {
+                io.px[p] = e.px[p];
+                io.py[p] = e.py[p];
+            }
+            io.active = active;
+            handle_events<TR>(c, &io);
+            status |= io.status;
+            x = io.x; y = io.y; th = io.th; vx = io.vx; vy = io.vy; om = io.om;
+            double gdummy[NEV];
+            event_values(c, e, x, y, om, gdummy, pd);
+            done = true;
+            break;
+        }
+#pragma unroll
+        for (int i = 0; i < NEV; ++i) g[i] = gn[i];
+        x = xn; y = yn; th = thn; vx = vxn; vy = vyn; om = omn;
+        A1x = A7x; A1y = A7y;
+        t = t_new;
+        if (t - T >= 0) break;  // scipy:base.py:199
+    }
+    // wrap_ship_angle (dynamic_model.py:179-180): numpy floor-mod by 2 pi
+    th = fmod(th, kTwoPi);
+    if (th < 0) th += kTwoPi;
+    if (!(isfinite(x) && isfinite(y) && isfinite(th) && isfinite(vx) && isfinite(vy) && isfinite(om))) status |= 8u;
+    e.x = x; e.y = y; e.th = th; e.vx = vx; e.vy = vy; e.om = om;
+    return done;
+}
+
+// ---- observation (spaceship_env.py:113-140, kepler.py:172-187) ---------------------------------------
+// Lidar = unit(obj - pos) * (|obj - pos| - r) * 2 / ws, written without atan2/cos/sin.
+template <class TR, typename OT>
+__device__ __forceinline__ void make_obs(const DevCfg& c, const EnvRegs<TR>& e, OT* row) {
+    double sn, cs;
+    sincos(e.th, &sn, &cs);
+    row[0] = (OT)e.x;
+    row[1] = (OT)e.y;
+    row[2] = (OT)cs;
+    row[3] = (OT)sn;
+    row[4] = (OT)e.vx;
+    row[5] = (OT)e.vy;
+    row[6] = (OT)e.om;
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int p = 0; p < TR::NP; ++p) {
+            double dx = e.px[p] - e.x, dy = e.py[p] - e.y;
+            double d2 = dx * dx + dy * dy;
+            double k = (1.0 - c.r0 * rsqrt(d2)) * c.two_over_ws;
+            row[7 + 2 * p] = (OT)(dx * k);
+            row[8 + 2 * p] = (OT)(dy * k);
+        }
+        row[7 + 2 * TR::NP] = (OT)((e.gx - e.x) * c.two_over_ws);
+        row[8 + 2 * TR::NP] = (OT)((e.gy - e.y) * c.two_over_ws);
+    } else {
+        row[7] = (OT)e.ang;
+        row[8] = (OT)e.ecc;
+        row[9] = (OT)c.orbit_a;
+    }
+}
+
+// ---- rewards ------------------------------------------------------------------------------------------
+// GoalEnv._reward without the sparse term (goal.py:147-165,204-227); cur = |goal - pos|.
+template <class TR>
+__device__ __forceinline__ double goal_reward(const DevCfg& c, const EnvRegs<TR>& e, double lx, double ly,
+                                              const double (&pd)[TR::NP], double& cur) {
+    double dx = e.gx - e.x, dy = e.gy - e.y;
+    cur = sqrt(dx * dx + dy * dy);
+    double ldx = e.gx - lx, ldy = e.gy - ly;
+    double last = sqrt(ldx * ldx + ldy * ldy);
+    double gv = (last - cur) * 100.0;
+    double mind = INFINITY, cx = 0, cy = 0;
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        bool closer = pd[p] < mind;
+        mind = closer ? pd[p] : mind;
+        cx = closer ? e.px[p] : cx;
+        cy = closer ? e.py[p] : cy;
+    }
+    double sum_safety = 0.0;
+    if (mind - c.r0 < c.danger_zone) {
+        double qx = lx - cx, qy = ly - cy;
+        double prev = sqrt(qx * qx + qy * qy);
+        if (prev > mind) sum_safety = -100.0 * (prev - mind);
+    }
+    return c.survival + c.goal_vel * gv + c.safety * sum_safety;
+}
+
+// KeplerEnv._dense_reward5 (kepler.py:43-150); atan2/cos replaced by the equivalent ratios.
+template <class TR>
+__device__ __forceinline__ double kepler_reward(const DevCfg& c, const EnvRegs<TR>& e, const Act& act) {
+    const double a = c.orbit_a, ecc = e.ecc;
+    double b = sqrt(a * a * (1 - ecc * ecc));
+    double cc = sqrt(a * a - b * b);
+    double sa, ca;
+    sincos(e.ang, &sa, &ca);
+    double w0 = ca * e.x + sa * e.y - cc;  // _rotate, then shift by the focal distance
+    double w1 = -sa * e.x + ca * e.y;
+    double nw2 = w0 * w0 + w1 * w1;
+    double inw = rsqrt(nw2);
+    double cur_rad = nw2 * inw;
+    double ecos = ecc * (w0 * inw);  // cos(atan2(w1, w0))
+    double target_rad = b * rsqrt(1 - ecos * ecos);
+    double p0 = w0 * target_rad * inw, p1 = w1 * target_rad * inw;  // projection onto the orbit
+    double v0 = -(a / b) * p1, v1 = (b / a) * p0;
+    double rx = p0 + cc;
+    double r = sqrt(rx * rx + p1 * p1);
+    double ov = sqrt(c.gm0 * (2 / r - 1 / a));  // vis-viva
+    double sc = ov * rsqrt(v0 * v0 + v1 * v1);
+    v0 *= sc;
+    v1 *= sc;
+    double t0 = ca * v0 - sa * v1;  // _rotate by -angle
+    double t1 = sa * v0 + ca * v1;
+    double den = c.radC * fabs(cur_rad - target_rad) + fabs(t0 - e.vx) + fabs(t1 - e.vy) + act.act_term + c.numC;
+    return c.numC / den;
+}
+
+// ---- hexagonal tiling state (hexagonal_tiling.py) ---------------------------------------------------------
+struct Tiles {
+    uint32_t case_b, flip_xy, ship_tile, goal_tile, n_free;  // goal_tile 63 = None
+    unsigned long long fw[4];                                // free multiset, 4 bits per entry
+    double cs[4];                                            // column shifts
+    __device__ uint32_t get(uint32_t k) const { return (uint32_t)(fw[k >> 4] >> ((k & 15u) * 4u)) & 15u; }
+    __device__ void set(uint32_t k, uint32_t v) {
+        unsigned long long m = 15ull << ((k & 15u) * 4u);
+        fw[k >> 4] = (fw[k >> 4] & ~m) | ((unsigned long long)v << ((k & 15u) * 4u));
+    }
+    __device__ uint32_t pack() const {
+        return case_b | (flip_xy << 1) | (ship_tile << 2) | (goal_tile << 8) | (n_free << 14);
+    }
+    __device__ void unpack(uint32_t w) {
+        case_b = w & 1u; flip_xy = (w >> 1) & 1u; ship_tile = (w >> 2) & 63u; goal_tile = (w >> 8) & 63u;
+        n_free = (w >> 14) & 127u;
+    }
+};
+
+__device__ inline void load_tiles(const DevCfg& c, long long i, Tiles& t) {
+    t.unpack(c.tile_word[i]);
+    for (int k = 0; k < 4; ++k) t.fw[k] = c.free_tiles[k * c.n + i];
+    for (int k = 0; k < c.cols; ++k) t.cs[k] = c.col_shift[k * c.n + i];
+}
+__device__ inline void store_tiles(const DevCfg& c, long long i, const Tiles& t, bool with_shift) {
+    c.tile_word[i] = t.pack();
+    for (int k = 0; k < 4; ++k) c.free_tiles[k * c.n + i] = t.fw[k];
+    if (with_shift)
+        for (int k = 0; k < c.cols; ++k) c.col_shift[k * c.n + i] = t.cs[k];
+}
+
+// HexagonalTiling._tile_center_pos (hexagonal_tiling.py:136-158)
+__device__ inline void tile_center(const DevCfg& c, const Tiles& t, int tile, double& ox, double& oy) {
+    int row = tile / c.cols, col = tile % c.cols;
+    double zero_x = -c.ws / 2 + c.hex_width / 2;
+    double zero_y = c.ws / 2 - c.hex_height / 2;
+    if (t.case_b) zero_y -= c.hex_height / 2;
+    double x_shift = col * 1.5 * c.hex_a + t.cs[col];
+    double y_rows = -row * c.hex_height;
+    double y_cols = -(col % 2) * c.hex_height / 2;
+    if (t.case_b) y_cols *= -1;
+    double cx = zero_x + x_shift, cy = zero_y + (y_rows + y_cols);
+    ox = t.flip_xy ? cy : cx;
+    oy = t.flip_xy ? cx : cy;
+}
+
+// choice(n, size=k, replace=False) as a partial Fisher-Yates (uniform ordered k-subset)
+__device__ inline void choice_no_replace(Rng& rng, int n, int k, int* out) {
+    int arr[64];
+    for (int i = 0; i < n; ++i) arr[i] = i;
+    for (int i = 0; i < k; ++i) {
+        int j = i + (int)(rng.uniform() * (n - i));
+        if (j > n - 1) j = n - 1;
+        int tmp = arr[i];
+        arr[i] = arr[j];
+        arr[j] = tmp;
+        out[i] = arr[i];
+    }
+}
+
+// HexagonalTiling.find_new_goal (hexagonal_tiling.py:95-134)
+__device__ inline void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double& gx, double& gy, uint32_t& status) {
+    if (t.goal_tile != 63u) {
+        if (t.n_free < 64u) {
+            t.set(t.n_free, t.ship_tile);
+            t.n_free += 1;
+        } else {
+            status |= 4u;  // SG_ENV_FREE_OVERFLOW
+        }
+        t.ship_tile = t.goal_tile;
+    }
+    if (rng.uniform() < 0.25) {
+        t.goal_tile = t.ship_tile;
+    } else {
+        int k = t.n_free < 3u ? (int)t.n_free : 3;
+        int cand[3];
+        choice_no_replace(rng, (int)t.n_free, k, cand);
+        int best = -1, best_idx = 0;
+        int srow = (int)t.ship_tile / c.cols, scol = (int)t.ship_tile % c.cols;
+        for (int i = 0; i < k; ++i) {
+            int tnr = (int)t.get((uint32_t)cand[i]);
+            int taxi = abs(tnr / c.cols - srow) + abs(tnr % c.cols - scol);
+            if (taxi > best) {
+                best = taxi;
+                best_idx = cand[i];
+            }
+        }
+        t.goal_tile = t.get((uint32_t)best_idx);
+        for (uint32_t i = (uint32_t)best_idx; i + 1 < t.n_free; ++i) t.set(i, t.get(i + 1));
+        t.n_free -= 1;
+    }
+    double cx, cy;
+    tile_center(c, t, (int)t.goal_tile, cx, cy);
+    double R = c.hex_height / 2 - c.goal_radius;
+    double ang = kTwoPi * rng.uniform();
+    double rr = sqrt(rng.uniform() * (R * R));
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    gx = cx + rr * cs;
+    gy = cy + rr * sn;
+}
+
+// Goal resample on a reached goal (goal.py:155-157): cold, touches the tile state in HBM.
+template <class TR>
+__device__ __noinline__ void resample_goal(const DevCfg& c, long long i, Rng* rng, double* gxy, uint32_t* status) {
+    Tiles t;
+    load_tiles(c, i, t);
+    find_new_goal(c, t, *rng, gxy[0], gxy[1], *status);
+    store_tiles(c, i, t, false);
+}
+
+// env.reset (goal.py:133-145 + hexagonal_tiling.py:53-93 | kepler.py:233-267).
+// out: x, y, th, vx, vy, om; Goal: planets (x0, y0, ...) at [6..], goal at [6+2P]; Kepler: (ecc, ang) at [6..7]
+// when randomize (left untouched otherwise).
+template <class TR>
+__device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, double* out, uint32_t* status) {
+    Rng& rng = *rngp;
+    if (TR::TASK == TASK_GOAL) {
+        constexpr int P = TR::NP;
+        const int n_tiles = c.rows * c.cols;
+        Tiles t;
+        for (int k = 0; k < 4; ++k) {
+            t.fw[k] = 0;
+            t.cs[k] = 0;
+        }
+        t.goal_tile = 63u;
+        t.case_b = rng.uniform() < 0.5;
+        t.flip_xy = rng.uniform() < 0.5;
+        double acc = 0;
+        for (int k = 0; k < c.cols; ++k) {
+            acc += rng.uniform();
+            t.cs[k] = acc;
+        }
+        double sc = c.free_x / t.cs[c.cols - 1];
+        for (int k = 0; k < c.cols; ++k) t.cs[k] *= sc;
+        int tiles[P + 1];
+        bool diag = false;
+        if (P == 2) diag = rng.uniform() < 0.25;
+        if (diag) {
+            const int cases[4][3] = {{1, 0, 3}, {2, 0, 3}, {0, 1, 2}, {3, 1, 2}};
+            int k = (int)(rng.uniform() * 4);
+            if (k > 3) k = 3;
+            for (int j = 0; j < 3 && j < P + 1; ++j) tiles[j] = cases[k][j];
+        } else {
+            choice_no_replace(rng, n_tiles, P + 1, tiles);
+        }
+        t.ship_tile = (uint32_t)tiles[0];
+        t.n_free = 0;
+        for (int k = 0; k < n_tiles; ++k) {
+            bool used = false;
+            for (int j = 0; j < P + 1; ++j) used |= (tiles[j] == k);
+            if (!used) {
+                t.set(t.n_free, (uint32_t)k);
+                t.n_free += 1;
+            }
+        }
+        double ang[P + 1];
+        for (int j = 0; j < P + 1; ++j) ang[j] = kTwoPi * rng.uniform();
+        for (int j = 0; j < P + 1; ++j) {
+            double radius = (j == 0) ? c.ship_radius : c.r0;
+            double R = c.hex_height / 2 - radius;
+            double rr = sqrt(rng.uniform() * (R * R));
+            double cx, cy, sn, cs;
+            tile_center(c, t, tiles[j], cx, cy);
+            sincos(ang[j], &sn, &cs);
+            double ox = cx + rr * cs, oy = cy + rr * sn;
+            if (j == 0) {
+                out[0] = ox;
+                out[1] = oy;
+            } else {
+                out[6 + 2 * (j - 1)] = ox;
+                out[7 + 2 * (j - 1)] = oy;
+            }
+        }
+        find_new_goal(c, t, rng, out[6 + 2 * P], out[7 + 2 * P], *status);
+        store_tiles(c, i, t, true);
+        out[2] = kTwoPi * rng.uniform();
+        out[3] = rng.normal() * 0.07;
+        out[4] = rng.normal() * 0.07;
+        double maxw = 0.7 * c.om_max;
+        double w = rng.normal() * maxw / 3;
+        out[5] = fmin(fmax(w, -maxw), maxw);
+    } else {
+        double pang = kTwoPi * rng.uniform();
+        double dist = c.kep_lo + (c.kep_hi - c.kep_lo) * rng.uniform();
+        double sn, cs;
+        sincos(pang, &sn, &cs);
+        out[0] = cs * dist;
+        out[1] = sn * dist;
+        out[2] = kTwoPi * rng.uniform();
+        if (c.randomize) {
+            out[6] = rng.uniform() * 0.7;
+            out[7] = rng.uniform() * 2 * kPi;
+        }
+        out[3] = rng.normal() * 0.05;
+        out[4] = rng.normal() * 0.05;
+        double maxw = 0.7 * c.om_max;
+        double w = rng.normal() * maxw / 5;
+        out[5] = fmin(fmax(w, -maxw), maxw);
+    }
+}
+
+}  // namespace sg

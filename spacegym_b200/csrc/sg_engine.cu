@@ -1,0 +1,873 @@
+// sg_engine.cu — kernels and C ABI (include/spacegym_b200.h) of the B200-native batched
+// Space-Gym stepping engine.  sm_100a only; no CPU path.
+//
+// Kernels
+//   step_kernel<TR, OT>    K fused env.step()s per launch, one thread per env: action translate ->
+//                          RK45 with events -> observation -> reward (+ goal resample) -> TimeLimit
+//                          -> auto-reset, state in registers across the K substeps; observation rows
+//                          staged in shared memory and written with 128-bit coalesced stores.
+//   reset_kernel<TR, OT>   (masked) env.reset(): hexagonal-tiling placement / Kepler draw from the
+//                          per-env Philox stream.
+//   vector_field_kernel    SpaceshipEnv.vector_field for every env.
+//   dfma_peak_kernel       FP64 roof micro-benchmark.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/spacegym_b200.h"
+#include "sg_device.cuh"
+
+namespace sg {
+
+constexpr int kBlock = 128;
+
+// ---- state access ---------------------------------------------------------------------------
+template <class TR>
+__device__ __forceinline__ void load_env(const DevCfg& c, long long i, EnvRegs<TR>& e) {
+    const long long n = c.n;
+    e.x = c.ship[i];
+    e.y = c.ship[n + i];
+    e.th = c.ship[2 * n + i];
+    e.vx = c.ship[3 * n + i];
+    e.vy = c.ship[4 * n + i];
+    e.om = c.ship[5 * n + i];
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int p = 0; p < TR::NP; ++p) {
+            e.px[p] = c.planets[(2 * p) * n + i];
+            e.py[p] = c.planets[(2 * p + 1) * n + i];
+        }
+        e.gx = c.goal[i];
+        e.gy = c.goal[n + i];
+        e.ecc = e.ang = 0.0;
+    } else {
+        e.px[0] = 0.0;  // kepler.py:204-206: planet and border sit at the origin
+        e.py[0] = 0.0;
+        e.gx = e.gy = 0.0;
+        e.ecc = c.orbit[i];
+        e.ang = c.orbit[n + i];
+    }
+}
+
+template <class TR>
+__device__ __forceinline__ void store_ship(const DevCfg& c, long long i, const EnvRegs<TR>& e) {
+    const long long n = c.n;
+    c.ship[i] = e.x;
+    c.ship[n + i] = e.y;
+    c.ship[2 * n + i] = e.th;
+    c.ship[3 * n + i] = e.vx;
+    c.ship[4 * n + i] = e.vy;
+    c.ship[5 * n + i] = e.om;
+}
+
+template <class TR>
+__device__ __forceinline__ void store_scene(const DevCfg& c, long long i, const EnvRegs<TR>& e, bool planets) {
+    const long long n = c.n;
+    if (TR::TASK == TASK_GOAL) {
+        if (planets) {
+#pragma unroll
+            for (int p = 0; p < TR::NP; ++p) {
+                c.planets[(2 * p) * n + i] = e.px[p];
+                c.planets[(2 * p + 1) * n + i] = e.py[p];
+            }
+        }
+        c.goal[i] = e.gx;
+        c.goal[n + i] = e.gy;
+    } else if (planets) {
+        c.orbit[i] = e.ecc;
+        c.orbit[n + i] = e.ang;
+    }
+}
+
+// copy the result of reset_env (sg_device.cuh) into the registers
+template <class TR>
+__device__ __forceinline__ void adopt_reset(const DevCfg& c, EnvRegs<TR>& e, const double* out) {
+    e.x = out[0]; e.y = out[1]; e.th = out[2]; e.vx = out[3]; e.vy = out[4]; e.om = out[5];
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int p = 0; p < TR::NP; ++p) {
+            e.px[p] = out[6 + 2 * p];
+            e.py[p] = out[7 + 2 * p];
+        }
+        e.gx = out[6 + 2 * TR::NP];
+        e.gy = out[7 + 2 * TR::NP];
+    } else if (c.randomize) {
+        e.ecc = out[6];
+        e.ang = out[7];
+    }
+}
+
+// Block-cooperative copy of the staged observation rows: 128-bit stores, fully coalesced.
+template <typename OT, int D>
+__device__ __forceinline__ void flush_obs(const OT* sobs, OT* obs, long long block_first, long long n) {
+    long long rows = n - block_first;
+    if (rows > kBlock) rows = kBlock;
+    const long long total = rows * D;  // elements
+    OT* dst = obs + block_first * D;   // 16-byte aligned: kBlock * D * sizeof(OT) is a multiple of 16
+    constexpr int V = 16 / sizeof(OT);
+    const long long nvec = total / V;
+    const int4* s4 = reinterpret_cast<const int4*>(sobs);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (long long j = threadIdx.x; j < nvec; j += kBlock) d4[j] = s4[j];
+    for (long long j = nvec * V + threadIdx.x; j < total; j += kBlock) dst[j] = sobs[j];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- the hot kernel --------------------------------------------------------------------------
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock)
+step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned long long step0, OT* __restrict__ obs,
+            double* __restrict__ reward, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    constexpr int D = TR::D;
+    __shared__ __align__(16) OT sobs[kBlock * D];
+    __shared__ double sstat[4][kBlock / 32];
+    const long long block_first = (long long)blockIdx.x * kBlock;
+    const long long i = block_first + threadIdx.x;
+    const bool valid = i < c.n;
+    double st_ret = 0, st_len = 0, st_eps = 0, st_goal = 0;
+
+    if (valid) {
+        EnvRegs<TR> e;
+        load_env<TR>(c, i, e);
+        uint32_t elapsed = c.elapsed[i];
+        double ep_ret = c.ep_return[i];
+        uint32_t status = 0;
+        uint32_t rng_ctr = 0;
+        bool rng_open = false, scene_dirty = false, planets_dirty = false;
+        Rng rng;
+        const unsigned long long genv = (unsigned long long)(c.first_env + i);
+
+        for (int k = 0; k < K; ++k) {
+            float r0, r1;
+            if (actions) {
+                float2 a = reinterpret_cast<const float2*>(actions)[(long long)k * c.n + i];
+                r0 = a.x;
+                r1 = a.y;
+            } else {
+                random_action(c.seed, genv, step0 + (unsigned long long)k, TR::DISC != 0, r0, r1);
+            }
+            const Act act = translate_action<TR>(c, r0, r1);
+            const double lx = e.x, ly = e.y;  // env.last_xy (spaceship_env.py:74)
+            double pd[TR::NP];
+            bool dn = make_step<TR>(c, e, act, status, pd);
+            const bool last = (k == K - 1);
+            if (last && obs) make_obs<TR, OT>(c, e, sobs + threadIdx.x * D);  // before _reward: old goal (quirk 3)
+
+            double r;
+            bool reached = false;
+            if (TR::TASK == TASK_GOAL) {
+                double cur;
+                r = goal_reward<TR>(c, e, lx, ly, pd, cur);
+                reached = cur < c.goal_radius;
+            } else {
+                r = kepler_reward<TR>(c, e, act);
+            }
+            bool trunc = false;
+            elapsed += 1;
+            if (c.max_episode_steps > 0 && elapsed >= (uint32_t)c.max_episode_steps) {  // gym TimeLimit
+                trunc = !dn;
+                dn = true;
+            }
+            if (reached || (dn && c.auto_reset)) {  // cold: needs the env's RNG stream
+                if (!rng_open) {
+                    rng_ctr = c.rng_ctr[i];
+                    rng.open(c.seed, genv, rng_ctr);
+                    rng_open = true;
+                }
+            }
+            if (TR::TASK == TASK_GOAL && reached) {
+                r += c.sparse;
+                st_goal += 1;
+                double gxy[2];
+                rng.fresh_block();
+                resample_goal<TR>(c, i, &rng, gxy, &status);
+                e.gx = gxy[0];
+                e.gy = gxy[1];
+                scene_dirty = true;
+            }
+            ep_ret += r;
+            if (dn) {
+                st_ret += ep_ret;
+                st_len += (double)elapsed;
+                st_eps += 1;
+                if (c.auto_reset) {  // gym.vector (0.21): the returned observation is the reset one
+                    double out[8 + 2 * TR::NP];
+                    rng.fresh_block();
+                    reset_env<TR>(c, i, &rng, out, &status);
+                    adopt_reset<TR>(c, e, out);
+                    scene_dirty = planets_dirty = true;
+                    elapsed = 0;
+                    ep_ret = 0.0;
+                    if (last && obs) make_obs<TR, OT>(c, e, sobs + threadIdx.x * D);
+                }
+            }
+            if (reward) reward[(long long)k * c.n + i] = r;
+            if (done_out) done_out[(long long)k * c.n + i] = dn ? 1 : 0;
+            if (trunc_out) trunc_out[(long long)k * c.n + i] = trunc ? 1 : 0;
+        }
+        store_ship<TR>(c, i, e);
+        if (scene_dirty) store_scene<TR>(c, i, e, planets_dirty);
+        c.elapsed[i] = elapsed;
+        c.ep_return[i] = ep_ret;
+        if (rng_open) c.rng_ctr[i] = rng.ctr;
+        if (status) c.status[i] |= status;
+    }
+    if (obs) {
+        __syncthreads();
+        flush_obs<OT, D>(sobs, obs, block_first, c.n);
+    }
+    // episode statistics: warp shuffle -> shared -> one atomic per block and counter
+    st_ret = warp_sum(st_ret);
+    st_len = warp_sum(st_len);
+    st_eps = warp_sum(st_eps);
+    st_goal = warp_sum(st_goal);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sstat[0][warp] = st_ret;
+        sstat[1][warp] = st_len;
+        sstat[2][warp] = st_eps;
+        sstat[3][warp] = st_goal;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) s += sstat[threadIdx.x][w];
+        if (s != 0) atomicAdd(&c.stats[threadIdx.x], s);
+    }
+}
+
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock)
+reset_kernel(const DevCfg c, const uint8_t* __restrict__ mask, OT* __restrict__ obs) {
+    constexpr int D = TR::D;
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= c.n) return;
+    if (mask && !mask[i]) return;
+    EnvRegs<TR> e;
+    load_env<TR>(c, i, e);
+    Rng rng;
+    rng.open(c.seed, (unsigned long long)(c.first_env + i), c.rng_ctr[i]);
+    uint32_t status = 0;
+    double out[8 + 2 * TR::NP];
+    reset_env<TR>(c, i, &rng, out, &status);
+    adopt_reset<TR>(c, e, out);
+    store_ship<TR>(c, i, e);
+    store_scene<TR>(c, i, e, true);
+    c.elapsed[i] = 0;
+    c.ep_return[i] = 0.0;
+    c.rng_ctr[i] = rng.ctr;
+    if (status) c.status[i] |= status;
+    if (obs) {
+        OT row[D];
+        make_obs<TR, OT>(c, e, row);
+#pragma unroll
+        for (int j = 0; j < D; ++j) obs[i * D + j] = row[j];
+    }
+}
+
+// SpaceshipEnv.vector_field (spaceship_env.py:96-100): [vx, vy, omega, ax, ay, alpha]
+template <class TR>
+__global__ void __launch_bounds__(kBlock)
+vector_field_kernel(const DevCfg c, const float* __restrict__ actions, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= c.n) return;
+    EnvRegs<TR> e;
+    load_env<TR>(c, i, e);
+    float2 a = reinterpret_cast<const float2*>(actions)[i];
+    const Act act = translate_action<TR>(c, a.x, a.y);
+    double sn, cs, ax, ay;
+    sincos(e.th, &sn, &cs);
+    accel<TR>(c, e, e.x, e.y, cs, sn, act.fs, ax, ay);
+    double om = (TR::STEER == STEER_VEL) ? act.w : e.om;
+    out[i * 6 + 0] = e.vx;
+    out[i * 6 + 1] = e.vy;
+    out[i * 6 + 2] = om;
+    out[i * 6 + 3] = ax;
+    out[i * 6 + 4] = ay;
+    out[i * 6 + 5] = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
+}
+
+__global__ void fill_orbit_kernel(double* orbit, long long n, double ecc, double ang) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        orbit[i] = ecc;
+        orbit[n + i] = ang;
+    }
+}
+
+// FP64 roof: 8 independent DFMA chains per thread, no memory traffic.
+__global__ void dfma_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+           a7 = seed + 7;
+    const double m = 0.999999, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace sg
+
+// =================================================================================================
+// host side: C ABI
+// =================================================================================================
+using namespace sg;
+
+struct sg_env {
+    sg_config cfg;
+    sg_layout lay;
+    DevCfg dev;
+    int device;
+    uint64_t seed;
+    int64_t n, first_env;
+    void* state;
+    bool owns_state;
+    double* d_stats;
+    uint64_t step_count;
+    int64_t launches;
+    std::string err;
+    // staging for the *_host entry points
+    cudaStream_t hstream;
+    float* s_actions;
+    size_t s_actions_bytes;
+    void* s_obs;
+    double* s_reward;
+    uint8_t* s_done;
+    uint8_t* s_trunc;
+    size_t s_k;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(sg_env* env, int code, const std::string& msg) {
+    if (env) env->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define SG_CUDA(env, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            return fail(env, SG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));  \
+    } while (0)
+
+extern "C" const char* sg_version(void) { return "spacegym_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* sg_last_error(const sg_env* env) { return env ? env->err.c_str() : g_create_error.c_str(); }
+
+// hexagonal_tiling.py:161-174
+static void tiling_rows_cols_a(int min_tiles, double world_size, int* r_out, int* c_out, double* a_out) {
+    const double s3 = sqrt(3.0);
+    double r_ = sqrt(72 * s3 * min_tiles - 6 * s3 + 12) / 12 - 1.0 / 4 + s3 / 12;
+    int r = (int)ceil(r_), c;
+    for (;;) {
+        c = (int)floor(2 * s3 * r / 3 - 1.0 / 3 + s3 / 3);
+        if (r * c >= min_tiles) break;
+        ++r;
+    }
+    *r_out = r;
+    *c_out = c;
+    *a_out = 2 * s3 * world_size / (3 * (2 * r + 1));
+}
+
+extern "C" int sg_config_finalize(sg_config* cfg) {
+    if (!cfg) return SG_ERR_INVALID;
+    if (cfg->task == SG_TASK_GOAL) {
+        // goal.py:10,62-72 fix these regardless of kwargs
+        cfg->world_size = 3.0;
+        cfg->step_size = 0.07;
+        cfg->max_abs_vel_angle = 6.0;
+        const int P = cfg->n_planets;
+        if (P < 2 || P > SG_MAX_PLANETS) return SG_ERR_INVALID;  // n_planets = 1 is broken upstream
+        const int n_objects = P + 2;
+        const int min_tiles = (P == 2) ? n_objects : (int)ceil(n_objects / 0.6);  // hexagonal_tiling.py:26-29
+        int r, c;
+        double a;
+        tiling_rows_cols_a(min_tiles, cfg->world_size, &r, &c, &a);
+        if (r * c > 16 || c > SG_MAX_COLS) return SG_ERR_INVALID;
+        cfg->rows = r;
+        cfg->cols = c;
+        cfg->hex_a = a;
+        cfg->hex_height = a * sqrt(3.0);
+        cfg->hex_width = 2 * a;
+        cfg->tiling_width = 3 * a * (c - 1) / 2 + 2 * a;
+        double pr = cfg->hex_height / 2;
+        pr *= 0.75;  // PLANET_TILE_RATIO
+        cfg->planets_radius = pr;
+        cfg->goal_radius = cfg->ship_radius = pr / 2;
+    } else if (cfg->task == SG_TASK_KEPLER) {
+        cfg->n_planets = 2;
+        cfg->world_size = 2 * cfg->kepler_border_radius;  // kepler.py:216
+        cfg->max_abs_vel_angle = 6;
+        cfg->rows = cfg->cols = 0;
+        cfg->planets_radius = cfg->kepler_planet_radius;
+        cfg->goal_radius = cfg->ship_radius = 0;
+    } else {
+        return SG_ERR_INVALID;
+    }
+    if (cfg->ship_steering != SG_STEER_ACCELERATION && cfg->ship_steering != SG_STEER_VELOCITY) return SG_ERR_INVALID;
+    return SG_OK;
+}
+
+extern "C" int sg_config_from_id(const char* id, sg_config* cfg) {
+    if (!id || !cfg) return SG_ERR_INVALID;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->ship_mass = 1;
+    cfg->max_thruster_force = 0.05;
+    cfg->max_episode_steps = 500;
+    cfg->auto_reset = 1;
+    cfg->total_planets_mass = 1e9;  // goal.py:14
+    cfg->kepler_planet_mass = 6e8;  // kepler.py:204
+    cfg->kepler_planet_radius = 0.2;
+    cfg->kepler_border_radius = 3.0;
+    cfg->ship_moi = 0.01;
+    cfg->max_engine_force = 0.4;
+    cfg->ship_steering = SG_STEER_VELOCITY;
+    int P = 0, disc = 0;
+    if (!strcmp(id, "GoalContinuous2P-v0")) P = 2;
+    else if (!strcmp(id, "GoalContinuous3P-v0")) P = 3;
+    else if (!strcmp(id, "GoalContinuous4P-v0")) P = 4;
+    else if (!strcmp(id, "GoalDiscrete2-v0")) P = 2, disc = 1;  // keyboard_agent.py:29-74
+    else if (!strcmp(id, "GoalDiscrete3-v0")) P = 3, disc = 1;
+    else if (!strcmp(id, "GoalDiscrete4-v0")) P = 4, disc = 1;
+    if (P) {  // gym_space/__init__.py:26-72
+        cfg->task = SG_TASK_GOAL;
+        cfg->n_planets = P;
+        cfg->discrete = disc;
+        cfg->survival_reward_scale = 0.2;
+        cfg->goal_vel_reward_scale = 5.0;
+        cfg->safety_reward_scale = 10.0;
+        cfg->goal_sparse_reward = 5.0;
+        cfg->danger_zone = 0.25;
+        if (disc) cfg->max_engine_force = 1;
+        return sg_config_finalize(cfg);
+    }
+    cfg->task = SG_TASK_KEPLER;  // gym_space/__init__.py:76-146
+    cfg->rad_penalty_C = 2;
+    cfg->numerator_C = 0.01;
+    cfg->act_penalty_C = 0.5;
+    cfg->step_size = 0.07;
+    cfg->ref_orbit_a = 1.2;
+    if (!strcmp(id, "KeplerCircleOrbit-v0")) {
+        cfg->ref_orbit_eccentricity = 0;
+        cfg->ref_orbit_angle = 0;
+    } else if (!strcmp(id, "KeplerDiscrete-v0")) {  // keyboard_agent.py:10-27
+        cfg->discrete = 1;
+        cfg->max_episode_steps = 0;  // registered there without a TimeLimit
+    } else if (!strcmp(id, "KeplerEllipseEasy-v0")) {
+        cfg->ref_orbit_eccentricity = 0.5;
+        cfg->ref_orbit_angle = 0.8;
+    } else if (!strcmp(id, "KeplerEllipseHard-v0")) {
+        cfg->ref_orbit_eccentricity = 0.725;
+        cfg->ref_orbit_angle = 3.925;
+    } else if (!strcmp(id, "KeplerRandomOrbits-v0")) {
+        cfg->randomize = 1;
+        cfg->ref_orbit_eccentricity = 0.5;  // kepler.py:193-194 until the first reset
+        cfg->ref_orbit_angle = 3.75;
+    } else {
+        return SG_ERR_UNKNOWN_ID;
+    }
+    return sg_config_finalize(cfg);
+}
+
+extern "C" int sg_obs_dim(const sg_config* cfg) {
+    if (!cfg) return SG_ERR_INVALID;
+    return cfg->task == SG_TASK_GOAL ? 9 + 2 * cfg->n_planets : 10;
+}
+
+extern "C" int sg_state_layout(const sg_config* cfg, int64_t n, sg_layout* out) {
+    if (!cfg || !out || n <= 0) return SG_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->n_envs = n;
+    int64_t off = 0;
+    auto take = [&](int64_t rows, int64_t elem) {
+        int64_t at = off;
+        off += ((rows * n * elem + 255) / 256) * 256;
+        return at;
+    };
+    const bool goal = cfg->task == SG_TASK_GOAL;
+    out->ship = take(6, 8);
+    out->planets = take(goal ? 2 * cfg->n_planets : 0, 8);
+    out->goal = take(goal ? 2 : 0, 8);
+    out->orbit = take(goal ? 0 : 2, 8);
+    out->col_shift = take(goal ? cfg->cols : 0, 8);
+    out->ep_return = take(1, 8);
+    out->free_tiles = take(goal ? SG_FREE_WORDS : 0, 8);
+    out->tile_word = take(goal ? 1 : 0, 4);
+    out->elapsed = take(1, 4);
+    out->rng_ctr = take(1, 4);
+    out->status = take(1, 4);
+    out->total_bytes = off;
+    return SG_OK;
+}
+
+static void build_dev(sg_env* h) {
+    const sg_config& c = h->cfg;
+    DevCfg& d = h->dev;
+    memset(&d, 0, sizeof(d));
+    char* base = (char*)h->state;
+    d.ship = (double*)(base + h->lay.ship);
+    d.planets = (double*)(base + h->lay.planets);
+    d.goal = (double*)(base + h->lay.goal);
+    d.orbit = (double*)(base + h->lay.orbit);
+    d.col_shift = (double*)(base + h->lay.col_shift);
+    d.ep_return = (double*)(base + h->lay.ep_return);
+    d.free_tiles = (unsigned long long*)(base + h->lay.free_tiles);
+    d.tile_word = (uint32_t*)(base + h->lay.tile_word);
+    d.elapsed = (uint32_t*)(base + h->lay.elapsed);
+    d.rng_ctr = (uint32_t*)(base + h->lay.rng_ctr);
+    d.status = (uint32_t*)(base + h->lay.status);
+    d.stats = h->d_stats;
+    d.n = h->n;
+    d.first_env = h->first_env;
+    d.seed = h->seed;
+    d.max_episode_steps = c.max_episode_steps;
+    d.randomize = c.randomize;
+    d.auto_reset = c.auto_reset;
+    d.rows = c.rows;
+    d.cols = c.cols;
+    d.T = c.step_size;
+    d.half_ws = c.world_size / 2;
+    d.two_over_ws = 2 / c.world_size;
+    d.om_max = c.max_abs_vel_angle;
+    d.inv_mass = 1.0 / c.ship_mass;
+    d.moi = c.ship_moi;
+    d.max_engine = c.max_engine_force;
+    d.max_thruster = c.max_thruster_force;
+    d.max_engine_f32 = (float)c.max_engine_force;
+    d.max_thruster_f32 = (float)c.max_thruster_force;
+    if (c.task == SG_TASK_GOAL) {
+        d.gm0 = kG * c.ship_mass * (c.total_planets_mass / c.n_planets);  // helpers.py:33, goal.py:43
+        d.r0 = c.planets_radius;
+        d.r1 = 0;
+    } else {
+        d.gm0 = kG * c.ship_mass * c.kepler_planet_mass;
+        d.r0 = c.kepler_planet_radius;
+        d.r1 = c.kepler_border_radius;
+    }
+    d.survival = c.survival_reward_scale;
+    d.goal_vel = c.goal_vel_reward_scale;
+    d.safety = c.safety_reward_scale;
+    d.sparse = c.goal_sparse_reward;
+    d.danger_zone = c.danger_zone;
+    d.goal_radius = c.goal_radius;
+    d.ship_radius = c.ship_radius;
+    d.ws = c.world_size;
+    d.hex_a = c.hex_a;
+    d.hex_height = c.hex_height;
+    d.hex_width = c.hex_width;
+    d.free_x = c.world_size - c.tiling_width;
+    d.orbit_a = c.ref_orbit_a;
+    d.numC = c.numerator_C;
+    d.radC = c.rad_penalty_C;
+    d.actC = c.act_penalty_C;
+    d.actC_f32 = (float)c.act_penalty_C;
+    d.kep_lo = c.kepler_planet_radius + 0.5;  // kepler.py:235-237
+    d.kep_hi = c.kepler_border_radius - 0.5;
+}
+
+extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint64_t seed, int64_t first_env_index,
+                         void* d_state, sg_env** out) {
+    if (!cfg || !out || n_envs <= 0) return fail(nullptr, SG_ERR_INVALID, "sg_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, SG_ERR_NO_DEVICE, "sg_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, SG_ERR_INVALID, "sg_create: bad device index");
+    sg_config c = *cfg;
+    if (sg_config_finalize(&c) != SG_OK) return fail(nullptr, SG_ERR_INVALID, "sg_create: unsupported configuration");
+    SG_CUDA(nullptr, cudaSetDevice(device));
+    sg_env* h = new sg_env();
+    h->cfg = c;
+    h->device = device;
+    h->seed = seed;
+    h->n = n_envs;
+    h->first_env = first_env_index;
+    h->step_count = 0;
+    h->launches = 0;
+    h->hstream = nullptr;
+    h->s_actions = nullptr;
+    h->s_actions_bytes = 0;
+    h->s_obs = nullptr;
+    h->s_reward = nullptr;
+    h->s_done = h->s_trunc = nullptr;
+    h->s_k = 0;
+    sg_state_layout(&c, n_envs, &h->lay);
+    h->owns_state = (d_state == nullptr);
+    h->state = d_state;
+    cudaError_t err = cudaSuccess;
+    if (h->owns_state) err = cudaMalloc(&h->state, (size_t)h->lay.total_bytes);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&h->d_stats, 4 * sizeof(double));
+    if (err == cudaSuccess) err = cudaMemset(h->state, 0, (size_t)h->lay.total_bytes);
+    if (err == cudaSuccess) err = cudaMemset(h->d_stats, 0, 4 * sizeof(double));
+    if (err != cudaSuccess) {
+        std::string msg = std::string("sg_create: ") + cudaGetErrorString(err);
+        delete h;
+        return fail(nullptr, SG_ERR_CUDA, msg);
+    }
+    build_dev(h);
+    if (c.task == SG_TASK_KEPLER) {
+        int blocks = (int)((n_envs + 255) / 256);
+        fill_orbit_kernel<<<blocks, 256>>>(h->dev.orbit, n_envs, c.ref_orbit_eccentricity, c.ref_orbit_angle);
+        h->launches += 1;
+    }
+    err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        std::string msg = std::string("sg_create: ") + cudaGetErrorString(err);
+        delete h;
+        return fail(nullptr, SG_ERR_CUDA, msg);
+    }
+    *out = h;
+    return SG_OK;
+}
+
+extern "C" void sg_destroy(sg_env* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->owns_state && h->state) cudaFree(h->state);
+    if (h->d_stats) cudaFree(h->d_stats);
+    if (h->s_actions) cudaFree(h->s_actions);
+    if (h->s_obs) cudaFree(h->s_obs);
+    if (h->s_reward) cudaFree(h->s_reward);
+    if (h->s_done) cudaFree(h->s_done);
+    if (h->s_trunc) cudaFree(h->s_trunc);
+    if (h->hstream) cudaStreamDestroy(h->hstream);
+    delete h;
+}
+
+extern "C" int sg_get_layout(const sg_env* h, sg_layout* out) {
+    if (!h || !out) return SG_ERR_INVALID;
+    *out = h->lay;
+    return SG_OK;
+}
+extern "C" void* sg_state_ptr(const sg_env* h) { return h ? h->state : nullptr; }
+extern "C" uint64_t sg_step_count(const sg_env* h) { return h ? h->step_count : 0; }
+extern "C" int sg_set_step_count(sg_env* h, uint64_t s) {
+    if (!h) return SG_ERR_INVALID;
+    h->step_count = s;
+    return SG_OK;
+}
+extern "C" int64_t sg_kernel_launches(const sg_env* h) { return h ? h->launches : 0; }
+
+// ---- kernel dispatch over (task, planets, steering, action space, obs dtype) -------------------
+enum Op { OP_STEP, OP_RESET, OP_VFIELD };
+
+struct LaunchArgs {
+    Op op;
+    cudaStream_t stream;
+    const float* actions;
+    int K;
+    unsigned long long step0;
+    void* obs;
+    double* reward;
+    uint8_t* done;
+    uint8_t* trunc;
+    const uint8_t* mask;
+    double* vf_out;
+};
+
+template <class TR, typename OT>
+static void launch_typed(const sg_env* h, const LaunchArgs& a) {
+    const int blocks = (int)((h->n + kBlock - 1) / kBlock);
+    if (a.op == OP_STEP)
+        step_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.K, a.step0, (OT*)a.obs, a.reward, a.done,
+                                                             a.trunc);
+    else if (a.op == OP_RESET)
+        reset_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.mask, (OT*)a.obs);
+}
+
+template <class TR>
+static void launch_tr(const sg_env* h, const LaunchArgs& a) {
+    if (a.op == OP_VFIELD) {
+        const int blocks = (int)((h->n + kBlock - 1) / kBlock);
+        vector_field_kernel<TR><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.vf_out);
+        return;
+    }
+    if (h->cfg.obs_dtype == SG_OBS_F32) launch_typed<TR, float>(h, a);
+    else launch_typed<TR, double>(h, a);
+}
+
+template <int TASK, int NP>
+static void launch_np(const sg_env* h, const LaunchArgs& a) {
+    const bool vel = h->cfg.ship_steering == SG_STEER_VELOCITY;
+    const bool disc = h->cfg.discrete != 0;
+    if (vel && !disc) launch_tr<Traits<TASK, NP, STEER_VEL, 0>>(h, a);
+    else if (vel && disc) launch_tr<Traits<TASK, NP, STEER_VEL, 1>>(h, a);
+    else if (!vel && !disc) launch_tr<Traits<TASK, NP, STEER_ACC, 0>>(h, a);
+    else launch_tr<Traits<TASK, NP, STEER_ACC, 1>>(h, a);
+}
+
+static int launch(sg_env* h, const LaunchArgs& a) {
+    SG_CUDA(h, cudaSetDevice(h->device));
+    if (h->cfg.task == SG_TASK_KEPLER) launch_np<TASK_KEPLER, 1>(h, a);
+    else if (h->cfg.n_planets == 2) launch_np<TASK_GOAL, 2>(h, a);
+    else if (h->cfg.n_planets == 3) launch_np<TASK_GOAL, 3>(h, a);
+    else if (h->cfg.n_planets == 4) launch_np<TASK_GOAL, 4>(h, a);
+    else return fail(h, SG_ERR_INVALID, "unsupported n_planets");
+    h->launches += 1;
+    SG_CUDA(h, cudaGetLastError());
+    return SG_OK;
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+extern "C" int sg_reset(sg_env* h, const uint8_t* d_mask, void* d_obs, void* stream) {
+    if (!h) return SG_ERR_INVALID;
+    LaunchArgs a{};
+    a.op = OP_RESET;
+    a.stream = (cudaStream_t)stream;
+    a.mask = d_mask;
+    a.obs = d_obs;
+    return launch(h, a);
+}
+
+extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, double* d_reward, uint8_t* d_done,
+                       uint8_t* d_truncated, void* stream) {
+    if (!h || K <= 0) return SG_ERR_INVALID;
+    if (d_obs && !aligned16(d_obs)) return fail(h, SG_ERR_INVALID, "sg_step: d_obs must be 16-byte aligned");
+    if (d_actions && (((uintptr_t)d_actions) & 7u)) return fail(h, SG_ERR_INVALID, "sg_step: d_actions must be 8-byte aligned");
+    LaunchArgs a{};
+    a.op = OP_STEP;
+    a.stream = (cudaStream_t)stream;
+    a.actions = d_actions;
+    a.K = K;
+    a.step0 = h->step_count;
+    a.obs = d_obs;
+    a.reward = d_reward;
+    a.done = d_done;
+    a.trunc = d_truncated;
+    int rc = launch(h, a);
+    if (rc == SG_OK) h->step_count += (uint64_t)K;
+    return rc;
+}
+
+extern "C" int sg_vector_field(sg_env* h, const float* d_actions, double* d_out, void* stream) {
+    if (!h || !d_actions || !d_out) return SG_ERR_INVALID;
+    LaunchArgs a{};
+    a.op = OP_VFIELD;
+    a.stream = (cudaStream_t)stream;
+    a.actions = d_actions;
+    a.vf_out = d_out;
+    return launch(h, a);
+}
+
+static size_t obs_elem(const sg_env* h) { return h->cfg.obs_dtype == SG_OBS_F32 ? 4 : 8; }
+
+static int ensure_staging(sg_env* h, int K) {
+    SG_CUDA(h, cudaSetDevice(h->device));
+    if (!h->hstream) SG_CUDA(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    const size_t n = (size_t)h->n, D = (size_t)sg_obs_dim(&h->cfg);
+    if (!h->s_obs) SG_CUDA(h, cudaMalloc(&h->s_obs, n * D * obs_elem(h)));
+    if ((size_t)K > h->s_k) {
+        if (h->s_actions) cudaFree(h->s_actions);
+        if (h->s_reward) cudaFree(h->s_reward);
+        if (h->s_done) cudaFree(h->s_done);
+        if (h->s_trunc) cudaFree(h->s_trunc);
+        SG_CUDA(h, cudaMalloc((void**)&h->s_actions, (size_t)K * n * 2 * sizeof(float)));
+        SG_CUDA(h, cudaMalloc((void**)&h->s_reward, (size_t)K * n * sizeof(double)));
+        SG_CUDA(h, cudaMalloc((void**)&h->s_done, (size_t)K * n));
+        SG_CUDA(h, cudaMalloc((void**)&h->s_trunc, (size_t)K * n));
+        h->s_k = (size_t)K;
+    }
+    return SG_OK;
+}
+
+extern "C" int sg_reset_host(sg_env* h, void* h_obs) {
+    if (!h) return SG_ERR_INVALID;
+    int rc = ensure_staging(h, 1);
+    if (rc != SG_OK) return rc;
+    rc = sg_reset(h, nullptr, h_obs ? h->s_obs : nullptr, h->hstream);
+    if (rc != SG_OK) return rc;
+    if (h_obs)
+        SG_CUDA(h, cudaMemcpyAsync(h_obs, h->s_obs, (size_t)h->n * sg_obs_dim(&h->cfg) * obs_elem(h),
+                                   cudaMemcpyDeviceToHost, h->hstream));
+    SG_CUDA(h, cudaStreamSynchronize(h->hstream));
+    return SG_OK;
+}
+
+extern "C" int sg_step_host(sg_env* h, const float* h_actions, int K, void* h_obs, double* h_reward, uint8_t* h_done,
+                            uint8_t* h_truncated) {
+    if (!h || K <= 0) return SG_ERR_INVALID;
+    int rc = ensure_staging(h, K);
+    if (rc != SG_OK) return rc;
+    const size_t n = (size_t)h->n, kn = (size_t)K * n;
+    if (h_actions)
+        SG_CUDA(h, cudaMemcpyAsync(h->s_actions, h_actions, kn * 2 * sizeof(float), cudaMemcpyHostToDevice, h->hstream));
+    rc = sg_step(h, h_actions ? h->s_actions : nullptr, K, h_obs ? h->s_obs : nullptr, h_reward ? h->s_reward : nullptr,
+                 h_done ? h->s_done : nullptr, h_truncated ? h->s_trunc : nullptr, h->hstream);
+    if (rc != SG_OK) return rc;
+    if (h_obs)
+        SG_CUDA(h, cudaMemcpyAsync(h_obs, h->s_obs, n * sg_obs_dim(&h->cfg) * obs_elem(h), cudaMemcpyDeviceToHost,
+                                   h->hstream));
+    if (h_reward) SG_CUDA(h, cudaMemcpyAsync(h_reward, h->s_reward, kn * sizeof(double), cudaMemcpyDeviceToHost, h->hstream));
+    if (h_done) SG_CUDA(h, cudaMemcpyAsync(h_done, h->s_done, kn, cudaMemcpyDeviceToHost, h->hstream));
+    if (h_truncated) SG_CUDA(h, cudaMemcpyAsync(h_truncated, h->s_trunc, kn, cudaMemcpyDeviceToHost, h->hstream));
+    SG_CUDA(h, cudaStreamSynchronize(h->hstream));
+    return SG_OK;
+}
+
+extern "C" int sg_stats(sg_env* h, double out[4], void* stream) {
+    if (!h || !out) return SG_ERR_INVALID;
+    SG_CUDA(h, cudaSetDevice(h->device));
+    SG_CUDA(h, cudaMemcpyAsync(out, h->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SG_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return SG_OK;
+}
+
+extern "C" int sg_stats_reset(sg_env* h, void* stream) {
+    if (!h) return SG_ERR_INVALID;
+    SG_CUDA(h, cudaSetDevice(h->device));
+    SG_CUDA(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(double), (cudaStream_t)stream));
+    return SG_OK;
+}
+
+extern "C" int sg_measure_fp64_peak(int device, double ms, double* tflops_out) {
+    if (!tflops_out) return SG_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, SG_ERR_NO_DEVICE, "no CUDA device");
+    SG_CUDA(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SG_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    double* d_out = nullptr;
+    SG_CUDA(nullptr, cudaMalloc((void**)&d_out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    SG_CUDA(nullptr, cudaEventCreate(&e0));
+    SG_CUDA(nullptr, cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    int iters = 2000;
+    double best = 0;
+    dfma_peak_kernel<<<blocks, threads>>>(d_out, 200, 1.0);  // warm-up
+    SG_CUDA(nullptr, cudaDeviceSynchronize());
+    double spent = 0;
+    for (int rep = 0; rep < 64 && spent < ms; ++rep) {
+        SG_CUDA(nullptr, cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0 + rep);
+        SG_CUDA(nullptr, cudaEventRecord(e1));
+        SG_CUDA(nullptr, cudaEventSynchronize(e1));
+        float t = 0;
+        SG_CUDA(nullptr, cudaEventElapsedTime(&t, e0, e1));
+        spent += t;
+        double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        double tf = flops / (t * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops_out = best;
+    return SG_OK;
+}

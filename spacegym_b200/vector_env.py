@@ -1,0 +1,251 @@
+"""BatchedSpaceEnv — gym.vector-style front end of the CUDA engine.
+
+Mirrors the reference's env interface for N independent envs (SpaceshipEnv.reset/step/seed/
+vector_field, spaceship_env.py:59-100) with the same observation, action and reward layout,
+env ids and kwargs.  All state lives in one caller-owned torch uint8 block in HBM that the
+C library addresses directly (struct-of-arrays, see sg_layout); torch is used for memory,
+streams and torch.distributed only — every computation is in libspacegym_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import spaces
+from ._lib import SgLayout, check, lib
+from .registry import make_config
+
+
+def shard_range(total_envs, rank, world_size):
+    """Contiguous global env range of one rank: results are shard-count invariant."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+class BatchedSpaceEnv:
+    def __init__(self, env_id, num_envs, device="cuda:0", seed=0, first_env_index=0, **kwargs):
+        self._h = None
+        self.env_id = env_id
+        self.cfg = make_config(env_id, **kwargs)
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("spacegym_b200 runs on CUDA devices only (there is no CPU path)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device available: spacegym_b200 has no CPU fallback")
+        self._L = lib()
+        self.seed_value = int(seed)
+        self.first_env_index = int(first_env_index)
+        self.obs_dim = self._L.sg_obs_dim(C.byref(self.cfg))
+        self.obs_dtype = torch.float32 if self.cfg.obs_dtype == 1 else torch.float64
+        lay = SgLayout()
+        check(self._L.sg_state_layout(C.byref(self.cfg), self.num_envs, C.byref(lay)))
+        self.layout = lay
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        with torch.cuda.device(self.device):
+            self._state = torch.zeros(lay.total_bytes, dtype=torch.uint8, device=self.device)
+            h = C.c_void_p()
+            check(self._L.sg_create(C.byref(self.cfg), self.num_envs, dev_index, self.seed_value,
+                                    self.first_env_index, self._state.data_ptr(), C.byref(h)))
+        self._h = h
+        self._host = None
+        self._init_spaces()
+
+    # ---- spaces (spaceship_env.py:102-111,183-214; kepler.py:158-170) -------------------------
+    def _init_spaces(self):
+        if self.cfg.discrete:
+            self.single_action_space = spaces.Discrete(6)
+        else:
+            ones = np.ones(2, dtype=np.float32)
+            self.single_action_space = spaces.Box(-ones, ones)
+        if self.cfg.task == 0:
+            hi = [1.0, 1.0, 1.0, 1.0, np.inf, np.inf, 1.0] + 2 * (self.cfg.n_planets + 1) * [2 * np.sqrt(2)]
+            hi = np.array(hi, dtype=np.float32)
+            self.single_observation_space = spaces.Box(-hi, hi)
+        else:
+            hi = np.array([1.0, 1.0, 1.0, 1.0, np.inf, np.inf, 1.0, 2 * np.pi, 0.7, 2])
+            self.single_observation_space = spaces.Box(-hi, hi, np.dtype(np.float64))
+        self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
+
+    # ---- helpers --------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ptr(self, t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _check_dev(self, t, dtype, shape):
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise AssertionError(f"expected contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}, "
+                                 f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+
+    def _field(self, off, rows, dtype):
+        n = self.num_envs
+        nbytes = rows * n * torch.empty((), dtype=dtype).element_size()
+        return self._state[off:off + nbytes].view(dtype).view(rows, n)
+
+    # ---- gym.vector API ---------------------------------------------------------------------------
+    def seed(self, seed=None):
+        """env.seed (spaceship_env.py:92-94): streams are keyed (seed, global env index); takes effect now."""
+        raise NotImplementedError("pass seed= to the constructor; streams are counter-based per (seed, env)")
+
+    def reset(self, mask=None):
+        obs = torch.empty((self.num_envs, self.obs_dim), dtype=self.obs_dtype, device=self.device)
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self._L.sg_reset(self._h, self._ptr(mask), self._ptr(obs), self._stream()), self._h)
+        return obs
+
+    def step(self, actions, check_actions=False):
+        """obs [N, D], reward [N], done [N] (bool), info — one env.step for every env.
+
+        torch CUDA actions run the device path; numpy actions run the host-buffer path
+        (sg_step_host) and return numpy arrays."""
+        if isinstance(actions, np.ndarray):
+            return self._step_host(actions, check_actions)
+        obs, rew, done, info = self.step_many(actions[None] if actions.dim() == 2 else actions.view(1, -1, 2),
+                                              check_actions)
+        return obs, rew[0], done[0], {"TimeLimit.truncated": info["TimeLimit.truncated"][0]}
+
+    def step_many(self, actions=None, check_actions=False, K=None, want_obs=True):
+        """K fused steps in one launch. actions: f32 [K, N, 2] (discrete: [..., 0] holds the index) or
+        None with K given for synthetic random actions. Returns obs after the last step, reward [K, N],
+        done [K, N], info."""
+        n = self.num_envs
+        if actions is not None:
+            K = actions.shape[0]
+            self._check_dev(actions, torch.float32, (K, n, 2))
+            if check_actions:  # the reference asserts action_space.contains (spaceship_env.py:71)
+                if self.cfg.discrete:
+                    a0 = actions[..., 0]
+                    assert bool(((a0 >= 0) & (a0 <= 5) & (a0 == a0.floor())).all()), "action outside Discrete(6)"
+                else:
+                    assert bool(((actions >= -1) & (actions <= 1)).all()), "action outside Box(-1, 1)"
+        obs = torch.empty((n, self.obs_dim), dtype=self.obs_dtype, device=self.device) if want_obs else None
+        rew = torch.empty((K, n), dtype=torch.float64, device=self.device)
+        done = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        trunc = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        check(self._L.sg_step(self._h, self._ptr(actions), int(K), self._ptr(obs), self._ptr(rew), self._ptr(done),
+                              self._ptr(trunc), self._stream()), self._h)
+        return obs, rew, done.bool(), {"TimeLimit.truncated": trunc.bool()}
+
+    def rollout_random(self, K):
+        """K env steps with the engine's synthetic uniform actions; nothing but statistics comes back."""
+        check(self._L.sg_step(self._h, None, int(K), None, None, None, None, self._stream()), self._h)
+
+    def _step_host(self, actions, check_actions=False):
+        n, D = self.num_envs, self.obs_dim
+        if self._host is None:
+            np_obs = np.float32 if self.cfg.obs_dtype == 1 else np.float64
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+            self._host = dict(act=pin((n, 2), torch.float32), obs=pin((n, D), self.obs_dtype),
+                              rew=pin((n,), torch.float64), done=pin((n,), torch.uint8), trunc=pin((n,), torch.uint8))
+            self._host_np = {k: v.numpy() for k, v in self._host.items()}
+            assert self._host_np["obs"].dtype == np_obs
+        hb, hn = self._host, self._host_np
+        a = np.asarray(actions)
+        if self.cfg.discrete and a.ndim == 1:
+            hn["act"][:, 0] = a
+            hn["act"][:, 1] = 0
+        else:
+            if check_actions:
+                assert a.shape == (n, 2) and np.all(a >= -1) and np.all(a <= 1), "action outside Box(-1, 1)"
+            hn["act"][...] = a.astype(np.float32, copy=False)
+        check(self._L.sg_step_host(self._h, self._ptr(hb["act"]), 1, self._ptr(hb["obs"]), self._ptr(hb["rew"]),
+                                   self._ptr(hb["done"]), self._ptr(hb["trunc"])), self._h)
+        return hn["obs"], hn["rew"], hn["done"].astype(bool), {"TimeLimit.truncated": hn["trunc"].astype(bool)}
+
+    def vector_field(self, actions):
+        """SpaceshipEnv.vector_field (spaceship_env.py:96-100) for every env: [N, 6]."""
+        self._check_dev(actions, torch.float32, (self.num_envs, 2))
+        out = torch.empty((self.num_envs, 6), dtype=torch.float64, device=self.device)
+        check(self._L.sg_vector_field(self._h, self._ptr(actions), self._ptr(out), self._stream()), self._h)
+        return out
+
+    # ---- state access (parity tests, checkpoints) ------------------------------------------------
+    def state_views(self):
+        """Zero-copy [rows, N] views of the struct-of-arrays state block."""
+        lay, c = self.layout, self.cfg
+        v = {"ship": self._field(lay.ship, 6, torch.float64),
+             "ep_return": self._field(lay.ep_return, 1, torch.float64),
+             "elapsed": self._field(lay.elapsed, 1, torch.int32),
+             "rng_ctr": self._field(lay.rng_ctr, 1, torch.int32),
+             "status": self._field(lay.status, 1, torch.int32)}
+        if c.task == 0:
+            v["planets"] = self._field(lay.planets, 2 * c.n_planets, torch.float64)
+            v["goal"] = self._field(lay.goal, 2, torch.float64)
+            v["col_shift"] = self._field(lay.col_shift, c.cols, torch.float64)
+            v["free_tiles"] = self._field(lay.free_tiles, 4, torch.int64)
+            v["tile_word"] = self._field(lay.tile_word, 1, torch.int32)
+        else:
+            v["orbit"] = self._field(lay.orbit, 2, torch.float64)
+        return v
+
+    def get_state(self):
+        """Env-major copies: ship [N, 6], planets [N, P, 2], goal [N, 2], orbit [N, 2] = (ecc, angle), ..."""
+        torch.cuda.current_stream(self.device).synchronize()
+        out = {}
+        for k, t in self.state_views().items():
+            t = t.t().contiguous()
+            if k == "planets":
+                t = t.view(self.num_envs, self.cfg.n_planets, 2)
+            elif t.shape[1] == 1:
+                t = t[:, 0].contiguous()
+            out[k] = t
+        out["step_count"] = int(self._L.sg_step_count(self._h))
+        return out
+
+    def set_state(self, state):
+        views = self.state_views()
+        for k, val in state.items():
+            if k == "step_count":
+                check(self._L.sg_set_step_count(self._h, int(val)), self._h)
+                continue
+            dst = views[k]
+            src = torch.as_tensor(val, device=self.device).to(dst.dtype)
+            src = src.reshape(self.num_envs, -1).t()
+            dst.copy_(src)
+
+    # ---- statistics ---------------------------------------------------------------------------------
+    def stats(self, allreduce=False):
+        """{'return_sum', 'length_sum', 'episodes', 'goals'} since creation / the last stats_reset().
+        allreduce=True sums over torch.distributed ranks (the only collective of the engine)."""
+        buf = (C.c_double * 4)()
+        check(self._L.sg_stats(self._h, buf, self._stream()), self._h)
+        vals = torch.tensor(list(buf), dtype=torch.float64)
+        if allreduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            if torch.distributed.get_backend() == "nccl":
+                vals = vals.to(self.device)
+            torch.distributed.all_reduce(vals)
+            vals = vals.cpu()
+        return dict(zip(("return_sum", "length_sum", "episodes", "goals"), vals.tolist()))
+
+    def stats_reset(self):
+        check(self._L.sg_stats_reset(self._h, self._stream()), self._h)
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.sg_kernel_launches(self._h))
+
+    @property
+    def step_count(self):
+        return int(self._L.sg_step_count(self._h))
+
+    def close(self):
+        if self._h is not None:
+            torch.cuda.synchronize(self.device)
+            self._L.sg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make(env_id, num_envs, **kwargs):
+    """gym.make analogue for the batched engine."""
+    return BatchedSpaceEnv(env_id, num_envs, **kwargs)
