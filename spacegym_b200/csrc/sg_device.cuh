@@ -672,8 +672,11 @@ __device__ __forceinline__ double goal_reward(const DevCfg& c, const EnvRegs<TR>
 template <class TR>
 __device__ __forceinline__ double kepler_reward(const DevCfg& c, const EnvRegs<TR>& e, const Act& act) {
     const double a = c.orbit_a, ecc = e.ecc;
-    double b = sqrt(a * a * (1 - ecc * ecc));
-    double cc = sqrt(a * a - b * b);
+    // no FMA contraction here: for a circular orbit a*a - b*b must cancel to exactly 0 as it does in
+    // the reference (a fused a*a - b*b leaves the rounding error of b*b, and its sqrt is ~3e-9)
+    const double aa = __dmul_rn(a, a);
+    double b = sqrt(__dmul_rn(aa, __dsub_rn(1.0, __dmul_rn(ecc, ecc))));
+    double cc = sqrt(__dsub_rn(aa, __dmul_rn(b, b)));
     double sa, ca;
     sincos(e.ang, &sa, &ca);
     double w0 = ca * e.x + sa * e.y - cc;  // _rotate, then shift by the focal distance
@@ -787,6 +790,7 @@ __device__ inline void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double
         t.goal_tile = t.get((uint32_t)best_idx);
         for (uint32_t i = (uint32_t)best_idx; i + 1 < t.n_free; ++i) t.set(i, t.get(i + 1));
         t.n_free -= 1;
+        t.set(t.n_free, 0u);  // keep vacated entries zero: the packed words are then canonical
     }
     double cx, cy;
     tile_center(c, t, (int)t.goal_tile, cx, cy);
