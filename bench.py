@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the batched Space-Gym stepping engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the config the north-star target is quoted on):
+GoalContinuous3P-v0, 262144 envs per step and per GPU, auto-reset with hexagonal-tiling
+placement, TimeLimit 500, uniform random float32 actions.  A "step" is one env.step() of one
+batch of 262144 envs (one `sg_step` launch, K=1: actions read from HBM, observation, reward
+and done written to HBM).  Four independent env batches are stepped round-robin so that the
+working set (4 x 86 MB state+outputs) exceeds the 126 MB L2 between revisits.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed (CUDA events, max over ranks) whole-job
+env-steps/s with inputs resident in HBM; `e2e` = the same through BatchedSpaceEnv.step with
+host (pinned) numpy buffers, copies inside the timed region; `roofline` = algorithmic HBM
+bytes of the step kernel over its measured launch time against the measured copy bandwidth,
+`roofline_fp64` the same for algorithmic FP64 flops against a DFMA micro-benchmark run here;
+`cpu_baseline` = the C oracle port on this box's host cores.
+
+`--impl reference` times the CPU implementation (oracle port, all host threads) on the same
+workload and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_ID = "GoalContinuous3P-v0"
+ENVS_PER_STEP = 262144
+N_BATCHES = 4
+ACTION_SETS = 4
+# SURVEY.md §8d contract figures for GoalContinuous3P-v0 (per env step, K=1, f64 observation)
+ALGO_BYTES_PER_STEP = 329.0
+ALGO_FLOPS_PER_STEP = 1215.0
+METRIC = "env-steps/sec (batched, device-timed)"
+UNIT = "env-steps/s"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(total_budget_s=12.0, n_envs=65536):
+    """The oracle port (plain C, OpenMP over envs) on the host cores, bounded sample of the same workload."""
+    from oracle import sg_oracle
+    cores = len(os.sched_getaffinity(0))
+    cfg = sg_oracle.config_from_id(ENV_ID)
+    eng = sg_oracle.Engine(cfg, n_envs, seed=1, n_threads=cores)
+    eng.reset()
+    eng.step(None, K=2)
+    t0 = time.perf_counter()
+    eng.step(None, K=4)
+    probe = (time.perf_counter() - t0) / 4
+    steps = max(4, min(2000, int(total_budget_s / max(probe, 1e-6))))
+    t0 = time.perf_counter()
+    eng.step(None, K=steps)
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{ENV_ID}, {n_envs} envs x {steps} steps, auto-reset, in-engine random actions, "
+                      f"oracle/sg_oracle.c with {cores} OpenMP threads ({dt:.1f} s)"}
+
+
+def run_reference(args):
+    """Reference arm: CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import sg_oracle
+    cores = len(os.sched_getaffinity(0))
+    cfg = sg_oracle.config_from_id(ENV_ID)
+    n = ENVS_PER_STEP
+    eng = sg_oracle.Engine(cfg, n, seed=1, n_threads=cores)
+    eng.reset()
+    rng = np.random.RandomState(0)
+    acts = [rng.uniform(-1, 1, size=(1, n, 2)).astype(np.float32) for _ in range(ACTION_SETS)]
+    t0 = time.perf_counter()
+    eng.step(acts[0])
+    probe = time.perf_counter() - t0
+    # bounded sample: shrink the batch if K steps of 262144 envs would take more than ~2 minutes
+    if probe * (args.steps + args.warmup) > 120:
+        n = max(4096, int(n * 120 / (probe * (args.steps + args.warmup))) // 4096 * 4096)
+        eng = sg_oracle.Engine(cfg, n, seed=1, n_threads=cores)
+        eng.reset()
+        acts = [a[:, :n].copy() for a in acts]
+    for w in range(args.warmup):
+        eng.step(acts[w % ACTION_SETS])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        eng.step(acts[k % ACTION_SETS])
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{ENV_ID}, {n} envs per step, {args.steps} steps, host numpy actions, oracle port, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{ENV_ID} {n} envs/step auto-reset TimeLimit500 random actions (CPU oracle port)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import spacegym_b200 as sg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (spacegym_b200 has no CPU path; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.envs
+    total = n * world
+    # envs sharded by contiguous global index range, no data-path collective
+    envs = [sg.make(ENV_ID, n, device=dev, seed=1000 + b, first_env_index=rank * n) for b in range(N_BATCHES)]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = [[(torch.rand((1, n, 2), device=dev, generator=gen) * 2 - 1).float().contiguous()
+                for _ in range(ACTION_SETS)] for _ in range(N_BATCHES)]
+    D = envs[0].obs_dim
+    outs = [dict(obs=torch.empty((n, D), dtype=torch.float64, device=dev),
+                 rew=torch.empty((1, n), dtype=torch.float64, device=dev),
+                 done=torch.empty((1, n), dtype=torch.uint8, device=dev),
+                 trunc=torch.empty((1, n), dtype=torch.uint8, device=dev)) for _ in range(N_BATCHES)]
+    for e in envs:
+        e.reset()
+    L = envs[0]._L
+    stream = torch.cuda.current_stream(dev)
+
+    def one_step(k):
+        b = k % N_BATCHES
+        e, o = envs[b], outs[b]
+        a = actions[b][(k // N_BATCHES) % ACTION_SETS]
+        rc = L.sg_step(e._h, a.data_ptr(), 1, o["obs"].data_ptr(), o["rew"].data_ptr(), o["done"].data_ptr(),
+                       o["trunc"].data_ptr(), stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError(L.sg_last_error(e._h))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(max(args.warmup, 3)):
+        one_step(k)
+    launches0 = sum(e.kernel_launches for e in envs)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for k in range(args.steps):
+        one_step(k)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    launches = sum(e.kernel_launches for e in envs) - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total * args.steps / (ms * 1e-3)
+
+    # ---- end to end: public API with host buffers (pinned), copies inside the timed region ----
+    e2e_steps = max(3, min(args.steps, 30))
+    host_acts = [np.random.RandomState(7 + rank + i).uniform(-1, 1, size=(n, 2)).astype(np.float32)
+                 for i in range(ACTION_SETS)]
+    for k in range(3):
+        envs[k % N_BATCHES].step(host_acts[k % ACTION_SETS])
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for k in range(e2e_steps):
+        obs, rew, done, info = envs[k % N_BATCHES].step(host_acts[k % ACTION_SETS])
+        checksum += float(rew[0])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total * e2e_steps / float(te.item())
+    h2d = n * 2 * 4
+    d2h = n * (D * 8 + 8 + 1 + 1)
+
+    stats = envs[0].stats(allreduce=world > 1)  # the engine's only collective: episode statistics
+
+    if rank == 0:
+        hbm_peak, peak_src = read_peaks()
+        launch_s = ms * 1e-3 / args.steps  # the timed region is exactly K step_kernel launches on this stream
+        achieved_gbs = ALGO_BYTES_PER_STEP * n / launch_s / 1e9
+        tf = C_double()
+        rc = L.sg_measure_fp64_peak(local, 300.0, tf.ref)
+        fp64_peak = tf.value if rc == 0 else None
+        fp64_ach = ALGO_FLOPS_PER_STEP * n / launch_s / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{ENV_ID} {n} envs/step/GPU auto-reset hexagonal-tiling TimeLimit500 "
+                                   f"random f32 actions, K=1 (one sg_step launch per step)",
+                       "envs_per_gpu_per_step": n, "total_envs_per_step": total,
+                       "l2": f"inputs larger than L2: {N_BATCHES} env batches stepped round-robin "
+                             f"({N_BATCHES * n * (ALGO_BYTES_PER_STEP + 60) / 1e6:.0f} MB working set)",
+                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "sg::step_kernel<Goal,3P,velocity,f64>", "algo_bytes_per_env_step": ALGO_BYTES_PER_STEP,
+                         "launch_ms": launch_s * 1e3},
+            "roofline_fp64": {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": (fp64_ach / fp64_peak) if fp64_peak else None,
+                              "algo_flops_per_env_step": ALGO_FLOPS_PER_STEP,
+                              "peak_source": "sg_measure_fp64_peak (DFMA chains, this run)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "BatchedSpaceEnv.step(numpy) -> sg_step_host"},
+            "gpu_launches": launches * world,
+            "clocks": clocks,
+            "episode_stats": stats,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    for e in envs:
+        e.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+class C_double:
+    def __init__(self):
+        import ctypes
+        self._v = ctypes.c_double(0.0)
+        self.ref = ctypes.byref(self._v)
+
+    @property
+    def value(self):
+        return self._v.value
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
