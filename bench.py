@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -214,13 +214,19 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi's own start-up stalls the GPU for ~100 ms
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:
+            time.sleep(0.05)
     for k in range(max(args.warmup, 3)):
         one_step(k)
     launches0 = sum(e.kernel_launches for e in envs)
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:
-        sampler.start()
+        sampler.rows.clear()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for k in range(args.steps):
@@ -322,7 +328,7 @@ class C_double:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
