@@ -45,6 +45,10 @@ extern "C" {
 enum sg_task { SG_TASK_GOAL = 0, SG_TASK_KEPLER = 1 };
 enum sg_steering { SG_STEER_ACCELERATION = 0, SG_STEER_VELOCITY = 1 }; /* ship_params.py:5-8 */
 enum sg_obs_dtype { SG_OBS_F64 = 0, SG_OBS_F32 = 1 };
+/* How sg_step maps onto kernels.  AUTO: K == 1 runs the split path (hot kernel + continuation and tail
+ * kernels fed by device-side work queues, warps stay converged); K > 1 runs the fused kernel (state in
+ * registers across the K substeps, rare paths inline). */
+enum sg_step_mode { SG_STEP_AUTO = 0, SG_STEP_FUSED = 1, SG_STEP_SPLIT = 2 };
 
 enum sg_status {
     SG_OK = 0,
@@ -70,6 +74,8 @@ typedef struct sg_config {
     int32_t randomize;         /* Kepler randomize */
     int32_t auto_reset;        /* 1: gym.vector semantics, done envs restart inside sg_step */
     int32_t obs_dtype;         /* sg_obs_dtype */
+    int32_t step_mode;         /* sg_step_mode */
+    int32_t reserved0;
     double ship_mass, ship_moi, max_engine_force, max_thruster_force;
     double world_size, max_abs_vel_angle, step_size;
     /* GoalEnv */

@@ -11,7 +11,7 @@ class SgConfig(C.Structure):
     _fields_ = [
         ("task", C.c_int32), ("n_planets", C.c_int32), ("ship_steering", C.c_int32), ("discrete", C.c_int32),
         ("max_episode_steps", C.c_int32), ("randomize", C.c_int32), ("auto_reset", C.c_int32),
-        ("obs_dtype", C.c_int32),
+        ("obs_dtype", C.c_int32), ("step_mode", C.c_int32), ("reserved0", C.c_int32),
         ("ship_mass", C.c_double), ("ship_moi", C.c_double), ("max_engine_force", C.c_double),
         ("max_thruster_force", C.c_double), ("world_size", C.c_double), ("max_abs_vel_angle", C.c_double),
         ("step_size", C.c_double),

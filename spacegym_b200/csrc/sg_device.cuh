@@ -92,6 +92,14 @@ struct DevCfg {
     uint32_t* rng_ctr;
     uint32_t* status;
     double* stats;  // 4 doubles: sum return, sum length, episodes, goals
+    // work queues of the split step path (library-owned scratch, empty between sg_step calls)
+    uint32_t* q_counts;   // [0] continuation, [1] event, [2] post, [3] block ticket
+    uint32_t* q_cont;     // env indices
+    uint32_t* q_event;
+    uint32_t* q_post;     // env index | reached << 30 | done << 31
+    double* scr_cont;     // [13][cap]: x y th vx vy om cth sth Ax Ay h_abs t flags(lx, ly separately)
+    double* scr_event;    // [24][cap]
+    long long q_cap;
     long long n;
     long long first_env;
     unsigned long long seed;
@@ -440,182 +448,284 @@ __device__ __noinline__ void handle_events(const DevCfg& c, EventIO<TR>* io) {
     d.eval(best, io->x, io->y, io->th, io->vx, io->vy, io->om);
 }
 
-// ---- one env.step of the physics: solve_ivp(RK45, (0, T), events) -----------------------------------
+// ---- integrator state carried between accepted steps ------------------------------------------------
+template <class TR>
+struct Integ {
+    double x, y, th, vx, vy, om;  // current state (omega already overwritten in velocity mode)
+    double cth, sth;              // cos / sin of th
+    double Ax, Ay;                // force evaluation at the current state (FSAL slot, K[0] of the next step)
+    double h_abs, t;              // solver.h_abs, solver.t
+    double alpha, fs;             // constant over the env step
+};
+
+// cos / sin of a small heading increment by Taylor polynomials (|d| < 0.5: error < 3e-17), so that the
+// stage headings cost a rotation of (cos th, sin th) instead of a full-range sincos each.
+__device__ __forceinline__ void small_sincos(double d, bool small, double& sn, double& cs) {
+    if (small) {
+        const double d2 = d * d;
+        double ps = fma(d2, 1.0 / 6227020800.0, -1.0 / 39916800.0);
+        ps = fma(ps, d2, 1.0 / 362880.0);
+        ps = fma(ps, d2, -1.0 / 5040.0);
+        ps = fma(ps, d2, 1.0 / 120.0);
+        ps = fma(ps, d2, -1.0 / 6.0);
+        sn = fma(ps * d2, d, d);
+        double pc = fma(d2, -1.0 / 87178291200.0, 1.0 / 479001600.0);
+        pc = fma(pc, d2, -1.0 / 3628800.0);
+        pc = fma(pc, d2, 1.0 / 40320.0);
+        pc = fma(pc, d2, -1.0 / 720.0);
+        pc = fma(pc, d2, 1.0 / 24.0);
+        pc = fma(pc, d2, -0.5);
+        cs = fma(pc, d2, 1.0);
+    } else {
+        sincos(d, &sn, &cs);
+    }
+}
+
+// force at (x, y) with the heading rotated by d from the step's base heading
+template <class TR>
+__device__ __forceinline__ void accel_rot(const DevCfg& c, const EnvRegs<TR>& e, const Integ<TR>& S, double x,
+                                          double y, double d, bool small, double& ax, double& ay, double& cn,
+                                          double& sn) {
+    double sd, cd;
+    small_sincos(d, small, sd, cd);
+    cn = S.cth * cd - S.sth * sd;
+    sn = S.sth * cd + S.cth * sd;
+    accel(c, e, x, y, cn, sn, S.fs, ax, ay);
+}
+
+// RK45.__init__ (scipy:rk.py:85-103): f0, select_initial_step (scipy:common.py:109-134, error estimator
+// order 4), and the event values at t0 (scipy:ivp.py:651, after the omega overwrite of quirk 1).
+template <class TR>
+__device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const Act& act, Integ<TR>& S,
+                                          double (&g)[TR::NEV], double (&pd)[TR::NP]) {
+    const double T = c.T;
+    S.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
+    S.fs = act.fs;
+    if (TR::STEER == STEER_VEL) e.om = act.w;  // the RHS overwrites omega in place
+    S.x = e.x; S.y = e.y; S.th = e.th; S.vx = e.vx; S.vy = e.vy; S.om = e.om;
+    S.t = 0.0;
+    sincos(S.th, &S.sth, &S.cth);
+    accel(c, e, S.x, S.y, S.cth, S.sth, S.fs, S.Ax, S.Ay);  // f0
+    const double x = S.x, y = S.y, th = S.th, vx = S.vx, vy = S.vy, om = S.om, alpha = S.alpha;
+    double rx = 1.0 / (kAtol + fabs(x) * kRtol), ry = 1.0 / (kAtol + fabs(y) * kRtol);
+    double rth = 1.0 / (kAtol + fabs(th) * kRtol), rvx = 1.0 / (kAtol + fabs(vx) * kRtol);
+    double rvy = 1.0 / (kAtol + fabs(vy) * kRtol), rom = 1.0 / (kAtol + fabs(om) * kRtol);
+    double q, S0 = 0, S1 = 0, S2 = 0;
+    q = x * rx; S0 = fma(q, q, S0);
+    q = y * ry; S0 = fma(q, q, S0);
+    q = th * rth; S0 = fma(q, q, S0);
+    q = vx * rvx; S0 = fma(q, q, S0);
+    q = vy * rvy; S0 = fma(q, q, S0);
+    q = om * rom; S0 = fma(q, q, S0);
+    q = vx * rx; S1 = fma(q, q, S1);
+    q = vy * ry; S1 = fma(q, q, S1);
+    q = om * rth; S1 = fma(q, q, S1);
+    q = S.Ax * rvx; S1 = fma(q, q, S1);
+    q = S.Ay * rvy; S1 = fma(q, q, S1);
+    q = alpha * rom; S1 = fma(q, q, S1);
+    double d0 = sqrt(S0) * kInvSqrt6, d1 = sqrt(S1) * kInvSqrt6;
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, T);
+    double Bx, By, cn, sn;
+    const double dprobe = h0 * om;
+    accel_rot(c, e, S, x + h0 * vx, y + h0 * vy, dprobe, fabs(dprobe) < 0.5, Bx, By, cn, sn);  // f(y0 + h0 f0)
+    q = h0 * S.Ax * rx; S2 = fma(q, q, S2);
+    q = h0 * S.Ay * ry; S2 = fma(q, q, S2);
+    q = h0 * alpha * rth; S2 = fma(q, q, S2);
+    q = (Bx - S.Ax) * rvx; S2 = fma(q, q, S2);
+    q = (By - S.Ay) * rvy; S2 = fma(q, q, S2);
+    double d2 = sqrt(S2) * kInvSqrt6 / h0;
+    const double dm = fmax(d1, d2);
+    const double lim = fmin(100 * h0, T);
+    double h_abs;
+    if (d1 <= 1e-15 && d2 <= 1e-15) {
+        h_abs = fmin(lim, fmax(1e-6, h0 * 1e-3));
+    } else {
+        // h1 = (0.01 / dm) ** 0.2 only matters when it is below lim: decide that without the pow
+        // (x -> x^5 is monotone), and pay for pow only on the lanes that need its value.
+        const double l2 = lim * lim;
+        if (0.01 >= dm * (l2 * l2 * lim) * 1.0000000001) h_abs = lim;
+        else h_abs = fmin(lim, pow(0.01 / dm, 0.2));
+    }
+    S.h_abs = h_abs;
+    event_values(c, e, x, y, om, g, pd);
+}
+
+// One Runge-Kutta attempt of size h from S (rk_step, scipy:rk.py:14-71) in Nystrom form, plus the error
+// norm (scipy:rk.py:105-109,141-143; the heading rows integrate exactly and contribute 0).
+template <class TR>
+__device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e, const Integ<TR>& S, double h,
+                                           double (&Ax)[7], double (&Ay)[7], double& xn, double& yn, double& thn,
+                                           double& vxn, double& vyn, double& omn, double& cn, double& sn,
+                                           double& err) {
+    const double x = S.x, y = S.y, vx = S.vx, vy = S.vy;
+    const double hh = h * h, ho = h * S.om, ha = hh * S.alpha;
+    const bool small = fabs(ho) + fabs(ha) < 0.5;
+    Ax[0] = S.Ax;
+    Ay[0] = S.Ay;
+    accel_rot(c, e, S, x + (c2 * h) * vx, y + (c2 * h) * vy, c2 * ho, small, Ax[1], Ay[1], cn, sn);
+    accel_rot(c, e, S, x + (c3 * h) * vx + hh * (ab31 * Ax[0]), y + (c3 * h) * vy + hh * (ab31 * Ay[0]),
+              c3 * ho + cs3 * ha, small, Ax[2], Ay[2], cn, sn);
+    accel_rot(c, e, S, x + (c4 * h) * vx + hh * (ab41 * Ax[0] + ab42 * Ax[1]),
+              y + (c4 * h) * vy + hh * (ab41 * Ay[0] + ab42 * Ay[1]), c4 * ho + cs4 * ha, small, Ax[3], Ay[3], cn, sn);
+    accel_rot(c, e, S, x + (c5 * h) * vx + hh * (ab51 * Ax[0] + ab52 * Ax[1] + ab53 * Ax[2]),
+              y + (c5 * h) * vy + hh * (ab51 * Ay[0] + ab52 * Ay[1] + ab53 * Ay[2]), c5 * ho + cs5 * ha, small, Ax[4],
+              Ay[4], cn, sn);
+    accel_rot(c, e, S, x + h * vx + hh * (ab61 * Ax[0] + ab62 * Ax[1] + ab63 * Ax[2] + ab64 * Ax[3]),
+              y + h * vy + hh * (ab61 * Ay[0] + ab62 * Ay[1] + ab63 * Ay[2] + ab64 * Ay[3]), ho + cs6 * ha, small,
+              Ax[5], Ay[5], cn, sn);
+    xn = x + h * vx + hh * (bb1 * Ax[0] + bb2 * Ax[1] + bb3 * Ax[2] + bb4 * Ax[3] + bb5 * Ax[4]);
+    yn = y + h * vy + hh * (bb1 * Ay[0] + bb2 * Ay[1] + bb3 * Ay[2] + bb4 * Ay[3] + bb5 * Ay[4]);
+    vxn = vx + h * (b1 * Ax[0] + b3 * Ax[2] + b4 * Ax[3] + b5 * Ax[4] + b6 * Ax[5]);
+    vyn = vy + h * (b1 * Ay[0] + b3 * Ay[2] + b4 * Ay[3] + b5 * Ay[4] + b6 * Ay[5]);
+    const double dth = ho + cs7 * ha;
+    thn = S.th + dth;
+    omn = S.om + h * S.alpha;
+    accel_rot(c, e, S, xn, yn, dth, small, Ax[6], Ay[6], cn, sn);  // f_new (FSAL)
+    double ex = hh * (eb1 * Ax[0] + eb2 * Ax[1] + eb3 * Ax[2] + eb4 * Ax[3] + eb5 * Ax[4] + eb6 * Ax[5]);
+    double ey = hh * (eb1 * Ay[0] + eb2 * Ay[1] + eb3 * Ay[2] + eb4 * Ay[3] + eb5 * Ay[4] + eb6 * Ay[5]);
+    double evx = h * (e1 * Ax[0] + e3 * Ax[2] + e4 * Ax[3] + e5 * Ax[4] + e6 * Ax[5] + e7 * Ax[6]);
+    double evy = h * (e1 * Ay[0] + e3 * Ay[2] + e4 * Ay[3] + e5 * Ay[4] + e6 * Ay[5] + e7 * Ay[6]);
+    ex /= kAtol + fmax(fabs(x), fabs(xn)) * kRtol;
+    ey /= kAtol + fmax(fabs(y), fabs(yn)) * kRtol;
+    evx /= kAtol + fmax(fabs(vx), fabs(vxn)) * kRtol;
+    evy /= kAtol + fmax(fabs(vy), fabs(vyn)) * kRtol;
+    err = sqrt(ex * ex + ey * ey + evx * evx + evy * evy) * kInvSqrt6;
+}
+
+__device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t, inf) - t|, scipy:rk.py:119
+    return 10 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+}
+
+// step-size controller after an attempt (scipy:rk.py:145-165); returns true when the step is accepted
+__device__ __forceinline__ bool controller(double err, bool& rejected, bool more_steps, double& h_abs) {
+    if (err < 1) {
+        if (more_steps) {  // the next step size only matters if another step follows
+            double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+            if (rejected) factor = fmin(1.0, factor);
+            h_abs *= factor;
+        }
+        return true;
+    }
+    h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+    rejected = true;
+    return false;
+}
+
+template <class TR>
+__device__ __forceinline__ uint32_t active_events(const double (&g)[TR::NEV], const double (&gn)[TR::NEV]) {
+    uint32_t active = 0;  // find_active_events, scipy:ivp.py:134-157 (direction 0)
+#pragma unroll
+    for (int i = 0; i < TR::NEV; ++i) {
+        bool up = (g[i] <= 0) && (gn[i] >= 0);
+        bool down = (g[i] >= 0) && (gn[i] <= 0);
+        if (up || down) active |= (1u << i);
+    }
+    return active;
+}
+
+template <class TR>
+__device__ __forceinline__ void fill_event_io(EventIO<TR>& io, const EnvRegs<TR>& e, const Integ<TR>& S, double h,
+                                              const double (&Ax)[7], const double (&Ay)[7], uint32_t active) {
+    io.x = S.x; io.y = S.y; io.th = S.th; io.vx = S.vx; io.vy = S.vy; io.om = S.om; io.alpha = S.alpha;
+    io.h = h; io.t_old = S.t;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        io.Ax[k] = Ax[k];
+        io.Ay[k] = Ay[k];
+    }
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        io.px[p] = e.px[p];
+        io.py[p] = e.py[p];
+    }
+    io.active = active;
+}
+
+enum { RK_FINISHED = 0, RK_EVENT = 1, RK_FAILED = 2 };
+
+// solve_ivp's loop (scipy:ivp.py:659-699 around RungeKutta._step_impl, scipy:rk.py:111-176) from the
+// integrator state S at time S.t.  `rejected` is the step_rejected flag of the attempt loop being resumed.
+// RK_EVENT: *io describes the accepted step in which a terminal event fired (roots still to be found).
+template <class TR>
+__device__ __forceinline__ int rk_loop(const DevCfg& c, const EnvRegs<TR>& e, Integ<TR>& S, double (&g)[TR::NEV],
+                                       bool rejected, EventIO<TR>* io, double (&pd)[TR::NP]) {
+    const double T = c.T;
+    for (;;) {
+        const double min_step = min_step_at(S.t);
+        if (S.h_abs < min_step && !rejected) S.h_abs = min_step;
+        double Ax[7], Ay[7], xn, yn, thn, vxn, vyn, omn, cn, sn, err, h, t_new;
+        for (;;) {
+            if (S.h_abs < min_step) return RK_FAILED;
+            t_new = S.t + S.h_abs;
+            if (t_new - T > 0) t_new = T;
+            h = t_new - S.t;
+            S.h_abs = fabs(h);
+            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err);
+            if (controller(err, rejected, t_new < T, S.h_abs)) break;
+        }
+        rejected = false;
+        double gn[TR::NEV];
+        event_values(c, e, xn, yn, omn, gn, pd);
+        const uint32_t active = active_events<TR>(g, gn);
+        if (active) {
+            fill_event_io<TR>(*io, e, S, h, Ax, Ay, active);
+            return RK_EVENT;
+        }
+#pragma unroll
+        for (int i = 0; i < TR::NEV; ++i) g[i] = gn[i];
+        S.x = xn; S.y = yn; S.th = thn; S.vx = vxn; S.vy = vyn; S.om = omn;
+        S.cth = cn; S.sth = sn;
+        S.Ax = Ax[6]; S.Ay = Ay[6];
+        S.t = t_new;
+        if (S.t - T >= 0) return RK_FINISHED;  // scipy:base.py:199
+    }
+}
+
+// wrap_ship_angle (dynamic_model.py:179-180): numpy floor-mod by 2 pi; also flags non-finite states
+__device__ __forceinline__ double wrap_angle(double th) {
+    th = fmod(th, kTwoPi);
+    if (th < 0) th += kTwoPi;
+    return th;
+}
+
+template <class TR>
+__device__ __forceinline__ void commit_state(EnvRegs<TR>& e, double x, double y, double th, double vx, double vy,
+                                             double om, uint32_t& status) {
+    th = wrap_angle(th);
+    if (!(isfinite(x) && isfinite(y) && isfinite(th) && isfinite(vx) && isfinite(vy) && isfinite(om))) status |= 8u;
+    e.x = x; e.y = y; e.th = th; e.vx = vx; e.vy = vy; e.om = om;
+}
+
+// ---- one env.step of the physics, everything inline (used by the K-fused kernel) ---------------------
 // Returns done.  On exit e holds the new state (heading wrapped) and pd the planet distances there.
 template <class TR>
 __device__ __forceinline__ bool make_step(const DevCfg& c, EnvRegs<TR>& e, const Act& act, uint32_t& status,
                                           double (&pd)[TR::NP]) {
-    constexpr int NEV = TR::NEV;
-    const double T = c.T;
-    const double alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
-    if (TR::STEER == STEER_VEL) e.om = act.w;  // the RHS overwrites omega in place (quirk 1)
-    double x = e.x, y = e.y, th = e.th, vx = e.vx, vy = e.vy, om = e.om;
-    const double fs = act.fs;
-
-    double sn, cs;
-    sincos(th, &sn, &cs);
-    double A1x, A1y;
-    accel(c, e, x, y, cs, sn, fs, A1x, A1y);  // f0
-
-    // select_initial_step (scipy:common.py:109-134), error_estimator_order = 4
-    double h_abs;
-    {
-        double rx = 1.0 / (kAtol + fabs(x) * kRtol), ry = 1.0 / (kAtol + fabs(y) * kRtol);
-        double rth = 1.0 / (kAtol + fabs(th) * kRtol), rvx = 1.0 / (kAtol + fabs(vx) * kRtol);
-        double rvy = 1.0 / (kAtol + fabs(vy) * kRtol), rom = 1.0 / (kAtol + fabs(om) * kRtol);
-        double q;
-        double S0 = 0, S1 = 0, S2 = 0;
-        q = x * rx; S0 = fma(q, q, S0);
-        q = y * ry; S0 = fma(q, q, S0);
-        q = th * rth; S0 = fma(q, q, S0);
-        q = vx * rvx; S0 = fma(q, q, S0);
-        q = vy * rvy; S0 = fma(q, q, S0);
-        q = om * rom; S0 = fma(q, q, S0);
-        q = vx * rx; S1 = fma(q, q, S1);
-        q = vy * ry; S1 = fma(q, q, S1);
-        q = om * rth; S1 = fma(q, q, S1);
-        q = A1x * rvx; S1 = fma(q, q, S1);
-        q = A1y * rvy; S1 = fma(q, q, S1);
-        q = alpha * rom; S1 = fma(q, q, S1);
-        double d0 = sqrt(S0) * kInvSqrt6, d1 = sqrt(S1) * kInvSqrt6;
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h0 = fmin(h0, T);
-        double s1, c1, Bx, By;
-        sincos(th + h0 * om, &s1, &c1);
-        accel(c, e, x + h0 * vx, y + h0 * vy, c1, s1, fs, Bx, By);  // f(y0 + h0 f0)
-        q = h0 * A1x * rx; S2 = fma(q, q, S2);
-        q = h0 * A1y * ry; S2 = fma(q, q, S2);
-        q = h0 * alpha * rth; S2 = fma(q, q, S2);
-        q = (Bx - A1x) * rvx; S2 = fma(q, q, S2);
-        q = (By - A1y) * rvy; S2 = fma(q, q, S2);
-        double d2 = sqrt(S2) * kInvSqrt6 / h0;
-        double h1;
-        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
-        else h1 = pow(0.01 / fmax(d1, d2), 0.2);
-        h_abs = fmin(fmin(100 * h0, h1), T);
-    }
-
-    double g[NEV];
-    event_values(c, e, x, y, om, g, pd);  // scipy:ivp.py:651 (after the omega overwrite)
-
-    double t = 0.0;
+    Integ<TR> S;
+    double g[TR::NEV];
+    init_step<TR>(c, e, act, S, g, pd);
+    EventIO<TR> io;
+    const int rc = rk_loop<TR>(c, e, S, g, false, &io, pd);
     bool done = false;
-    for (;;) {
-        // RungeKutta._step_impl (scipy:rk.py:111-176)
-        double min_step = 10 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false, failed = false;
-        double h, t_new, xn, yn, vxn, vyn, thn, omn;
-        double A2x, A2y, A3x, A3y, A4x, A4y, A5x, A5y, A6x, A6y, A7x, A7y;
-        for (;;) {
-            if (h_abs < min_step) {
-                failed = true;
-                break;
-            }
-            t_new = t + h_abs;
-            if (t_new - T > 0) t_new = T;
-            h = t_new - t;
-            h_abs = fabs(h);
-            const double hh = h * h, hv = h, ha = hh * alpha;
-            // rk_step (scipy:rk.py:14-71) in Nystrom form
-            sincos(th + (c2 * hv) * om, &sn, &cs);
-            accel(c, e, x + (c2 * hv) * vx, y + (c2 * hv) * vy, cs, sn, fs, A2x, A2y);
-            sincos(th + (c3 * hv) * om + cs3 * ha, &sn, &cs);
-            accel(c, e, x + (c3 * hv) * vx + hh * (ab31 * A1x), y + (c3 * hv) * vy + hh * (ab31 * A1y), cs, sn, fs, A3x,
-                  A3y);
-            sincos(th + (c4 * hv) * om + cs4 * ha, &sn, &cs);
-            accel(c, e, x + (c4 * hv) * vx + hh * (ab41 * A1x + ab42 * A2x),
-                  y + (c4 * hv) * vy + hh * (ab41 * A1y + ab42 * A2y), cs, sn, fs, A4x, A4y);
-            sincos(th + (c5 * hv) * om + cs5 * ha, &sn, &cs);
-            accel(c, e, x + (c5 * hv) * vx + hh * (ab51 * A1x + ab52 * A2x + ab53 * A3x),
-                  y + (c5 * hv) * vy + hh * (ab51 * A1y + ab52 * A2y + ab53 * A3y), cs, sn, fs, A5x, A5y);
-            sincos(th + hv * om + cs6 * ha, &sn, &cs);
-            accel(c, e, x + hv * vx + hh * (ab61 * A1x + ab62 * A2x + ab63 * A3x + ab64 * A4x),
-                  y + hv * vy + hh * (ab61 * A1y + ab62 * A2y + ab63 * A3y + ab64 * A4y), cs, sn, fs, A6x, A6y);
-            xn = x + hv * vx + hh * (bb1 * A1x + bb2 * A2x + bb3 * A3x + bb4 * A4x + bb5 * A5x);
-            yn = y + hv * vy + hh * (bb1 * A1y + bb2 * A2y + bb3 * A3y + bb4 * A4y + bb5 * A5y);
-            vxn = vx + h * (b1 * A1x + b3 * A3x + b4 * A4x + b5 * A5x + b6 * A6x);
-            vyn = vy + h * (b1 * A1y + b3 * A3y + b4 * A4y + b5 * A5y + b6 * A6y);
-            thn = th + hv * om + cs7 * ha;
-            omn = om + h * alpha;
-            sincos(thn, &sn, &cs);
-            accel(c, e, xn, yn, cs, sn, fs, A7x, A7y);  // f_new (FSAL)
-            // error norm (scipy:rk.py:105-109,141-143); the heading rows are exactly integrable -> 0
-            double ex = hh * (eb1 * A1x + eb2 * A2x + eb3 * A3x + eb4 * A4x + eb5 * A5x + eb6 * A6x);
-            double ey = hh * (eb1 * A1y + eb2 * A2y + eb3 * A3y + eb4 * A4y + eb5 * A5y + eb6 * A6y);
-            double evx = h * (e1 * A1x + e3 * A3x + e4 * A4x + e5 * A5x + e6 * A6x + e7 * A7x);
-            double evy = h * (e1 * A1y + e3 * A3y + e4 * A4y + e5 * A5y + e6 * A6y + e7 * A7y);
-            ex /= kAtol + fmax(fabs(x), fabs(xn)) * kRtol;
-            ey /= kAtol + fmax(fabs(y), fabs(yn)) * kRtol;
-            evx /= kAtol + fmax(fabs(vx), fabs(vxn)) * kRtol;
-            evy /= kAtol + fmax(fabs(vy), fabs(vyn)) * kRtol;
-            double err = sqrt(ex * ex + ey * ey + evx * evx + evy * evy) * kInvSqrt6;
-            if (err < 1) {
-                if (t_new < T) {  // the next step size only matters if another step follows
-                    double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
-                    if (rejected) factor = fmin(1.0, factor);
-                    h_abs *= factor;
-                }
-                break;
-            }
-            h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
-            rejected = true;
-        }
-        if (failed) {
-            status |= 1u;  // SG_ENV_STEP_TOO_SMALL
-            break;
-        }
-        // events at the accepted end point (scipy:ivp.py:679-699)
-        double gn[NEV];
-        event_values(c, e, xn, yn, omn, gn, pd);
-        uint32_t active = 0;
-#pragma unroll
-        for (int i = 0; i < NEV; ++i) {
-            bool up = (g[i] <= 0) && (gn[i] >= 0);
-            bool down = (g[i] >= 0) && (gn[i] <= 0);
-            if (up || down) active |= (1u << i);
-        }
-        if (active) {
-            EventIO<TR> io;
-            io.x = x; io.y = y; io.th = th; io.vx = vx; io.vy = vy; io.om = om; io.alpha = alpha;
-            io.h = h; io.t_old = t;
-            io.Ax[0] = A1x; io.Ax[1] = A2x; io.Ax[2] = A3x; io.Ax[3] = A4x; io.Ax[4] = A5x; io.Ax[5] = A6x; io.Ax[6] = A7x;
-            io.Ay[0] = A1y; io.Ay[1] = A2y; io.Ay[2] = A3y; io.Ay[3] = A4y; io.Ay[4] = A5y; io.Ay[5] = A6y; io.Ay[6] = A7y;
-#pragma unroll
-            for (int p = 0; p < TR::NP; ++p) {
-                io.px[p] = e.px[p];
-                io.py[p] = e.py[p];
-            }
-            io.active = active;
-            handle_events<TR>(c, &io);
-            status |= io.status;
-            x = io.x; y = io.y; th = io.th; vx = io.vx; vy = io.vy; om = io.om;
-            double gdummy[NEV];
-            event_values(c, e, x, y, om, gdummy, pd);
-            done = true;
-            break;
-        }
-#pragma unroll
-        for (int i = 0; i < NEV; ++i) g[i] = gn[i];
-        x = xn; y = yn; th = thn; vx = vxn; vy = vyn; om = omn;
-        A1x = A7x; A1y = A7y;
-        t = t_new;
-        if (t - T >= 0) break;  // scipy:base.py:199
+    if (rc == RK_EVENT) {
+        handle_events<TR>(c, &io);
+        status |= io.status;
+        commit_state<TR>(e, io.x, io.y, io.th, io.vx, io.vy, io.om, status);
+        double gdummy[TR::NEV];
+        event_values(c, e, e.x, e.y, e.om, gdummy, pd);
+        done = true;
+    } else {
+        if (rc == RK_FAILED) status |= 1u;  // SG_ENV_STEP_TOO_SMALL
+        commit_state<TR>(e, S.x, S.y, S.th, S.vx, S.vy, S.om, status);
     }
-    // wrap_ship_angle (dynamic_model.py:179-180): numpy floor-mod by 2 pi
-    th = fmod(th, kTwoPi);
-    if (th < 0) th += kTwoPi;
-    if (!(isfinite(x) && isfinite(y) && isfinite(th) && isfinite(vx) && isfinite(vy) && isfinite(om))) status |= 8u;
-    e.x = x; e.y = y; e.th = th; e.vx = vx; e.vy = vy; e.om = om;
     return done;
 }
 
 // ---- observation (spaceship_env.py:113-140, kepler.py:172-187) ---------------------------------------
 // Lidar = unit(obj - pos) * (|obj - pos| - r) * 2 / ws, written without atan2/cos/sin.
 template <class TR, typename OT>
-__device__ __forceinline__ void make_obs(const DevCfg& c, const EnvRegs<TR>& e, OT* row) {
-    double sn, cs;
-    sincos(e.th, &sn, &cs);
+__device__ __forceinline__ void make_obs_cs(const DevCfg& c, const EnvRegs<TR>& e, double cs, double sn, OT* row) {
     row[0] = (OT)e.x;
     row[1] = (OT)e.y;
     row[2] = (OT)cs;
@@ -639,6 +749,13 @@ __device__ __forceinline__ void make_obs(const DevCfg& c, const EnvRegs<TR>& e, 
         row[8] = (OT)e.ecc;
         row[9] = (OT)c.orbit_a;
     }
+}
+
+template <class TR, typename OT>
+__device__ __forceinline__ void make_obs(const DevCfg& c, const EnvRegs<TR>& e, OT* row) {
+    double sn, cs;
+    sincos(e.th, &sn, &cs);
+    make_obs_cs<TR, OT>(c, e, cs, sn, row);
 }
 
 // ---- rewards ------------------------------------------------------------------------------------------

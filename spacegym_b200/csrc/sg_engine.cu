@@ -245,6 +245,365 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
     }
 }
 
+// =================================================================================================
+// Split step path (K = 1): hot -> continuation -> tail, connected by global work queues.
+//
+// A 32-wide warp only runs at full width while its lanes do the same thing.  Per env step 79 % of the
+// envs need exactly one Runge-Kutta step, 21 % need more, ~2 % hit a terminal event (dense output +
+// Brent roots + reset) and ~0.3 % reach their goal (tile bookkeeping + RNG).  In one monolithic kernel
+// nearly every warp pays for all of these paths.  Here the hot kernel runs the common path for every
+// env (initial step selection + ONE attempt + epilogue) and appends the rest to compact queues, which
+// the continuation and tail kernels process with densely packed warps.
+// =================================================================================================
+constexpr int kContFields = 15;   // x y th vx vy om cth sth Ax Ay h_abs t lx ly rejected
+constexpr int kEventFields = 25;  // x y th vx vy om h t_old Ax[7] Ay[7] lx ly active
+constexpr uint32_t kPostReached = 1u << 30, kPostDone = 1u << 31, kPostIndex = (1u << 30) - 1;
+
+// warp-aggregated queue append; must be called by all 32 lanes of the warp
+__device__ __forceinline__ uint32_t queue_push(uint32_t* counter, bool need) {
+    const unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (mask == 0) return 0;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void block_stats_flush(const DevCfg& c, double (&st)[4]) {
+    __shared__ double sstat[4][BLOCK / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double v = warp_sum(st[k]);
+        if (lane == 0) sstat[k][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; ++w) s += sstat[threadIdx.x][w];
+        if (s != 0) atomicAdd(&c.stats[threadIdx.x], s);
+    }
+}
+
+template <class TR>
+__device__ __forceinline__ Act fetch_action(const DevCfg& c, const float* __restrict__ actions, long long i,
+                                            unsigned long long step0) {
+    float r0, r1;
+    if (actions) {
+        float2 a = reinterpret_cast<const float2*>(actions)[i];
+        r0 = a.x;
+        r1 = a.y;
+    } else {
+        random_action(c.seed, (unsigned long long)(c.first_env + i), step0, TR::DISC != 0, r0, r1);
+    }
+    return translate_action<TR>(c, r0, r1);
+}
+
+// Epilogue of an env whose physics is finished: observation (old goal, quirk 3), reward, TimeLimit,
+// bookkeeping and outputs.  The goal resample / reset are NOT done here (post work).
+template <class TR, typename OT>
+__device__ __forceinline__ void finish_env(const DevCfg& c, long long i, EnvRegs<TR>& e, const Act& act, double lx,
+                                           double ly, const double (&pd)[TR::NP], bool dn, OT* obs_row, double cs,
+                                           double sn, double* __restrict__ reward, uint8_t* __restrict__ done_out,
+                                           uint8_t* __restrict__ trunc_out, double (&st)[4], bool& reached,
+                                           bool& done) {
+    if (obs_row) make_obs_cs<TR, OT>(c, e, cs, sn, obs_row);
+    double r;
+    reached = false;
+    if (TR::TASK == TASK_GOAL) {
+        double cur;
+        r = goal_reward<TR>(c, e, lx, ly, pd, cur);
+        reached = cur < c.goal_radius;
+        if (reached) {
+            r += c.sparse;
+            st[3] += 1;
+        }
+    } else {
+        r = kepler_reward<TR>(c, e, act);
+    }
+    uint32_t elapsed = c.elapsed[i] + 1;
+    bool trunc = false;
+    if (c.max_episode_steps > 0 && elapsed >= (uint32_t)c.max_episode_steps) {  // gym TimeLimit
+        trunc = !dn;
+        dn = true;
+    }
+    const double ep_ret = c.ep_return[i] + r;
+    if (dn) {
+        st[0] += ep_ret;
+        st[1] += (double)elapsed;
+        st[2] += 1;
+    }
+    store_ship<TR>(c, i, e);
+    c.elapsed[i] = elapsed;
+    c.ep_return[i] = ep_ret;
+    if (reward) reward[i] = r;
+    if (done_out) done_out[i] = dn ? 1 : 0;
+    if (trunc_out) trunc_out[i] = trunc ? 1 : 0;
+    done = dn;
+}
+
+// Post work of a finished env: goal resample (goal.py:155-157) and/or auto-reset (gym.vector 0.21:
+// the returned observation becomes the reset one), both from the env's Philox stream.
+template <class TR, typename OT>
+__device__ __forceinline__ void post_env(const DevCfg& c, long long i, bool reached, bool done, OT* __restrict__ obs) {
+    Rng rng;
+    rng.open(c.seed, (unsigned long long)(c.first_env + i), c.rng_ctr[i]);
+    uint32_t status = 0;
+    if (TR::TASK == TASK_GOAL && reached) {
+        double gxy[2];
+        rng.fresh_block();
+        resample_goal<TR>(c, i, &rng, gxy, &status);
+        c.goal[i] = gxy[0];
+        c.goal[c.n + i] = gxy[1];
+    }
+    if (done && c.auto_reset) {
+        EnvRegs<TR> e;
+        load_env<TR>(c, i, e);
+        double out[8 + 2 * TR::NP];
+        rng.fresh_block();
+        reset_env<TR>(c, i, &rng, out, &status);
+        adopt_reset<TR>(c, e, out);
+        store_ship<TR>(c, i, e);
+        store_scene<TR>(c, i, e, true);
+        c.elapsed[i] = 0;
+        c.ep_return[i] = 0.0;
+        if (obs) {
+            OT row[TR::D];
+            make_obs<TR, OT>(c, e, row);
+#pragma unroll
+            for (int j = 0; j < TR::D; ++j) obs[i * TR::D + j] = row[j];
+        }
+    }
+    c.rng_ctr[i] = rng.ctr;
+    if (status) c.status[i] |= status;
+}
+
+template <class TR>
+__device__ __forceinline__ void save_cont(const DevCfg& c, uint32_t slot, long long i, const Integ<TR>& S, double lx,
+                                          double ly, bool rejected) {
+    const long long cap = c.q_cap;
+    double* p = c.scr_cont + slot;
+    c.q_cont[slot] = (uint32_t)i;
+    p[0 * cap] = S.x; p[1 * cap] = S.y; p[2 * cap] = S.th; p[3 * cap] = S.vx; p[4 * cap] = S.vy; p[5 * cap] = S.om;
+    p[6 * cap] = S.cth; p[7 * cap] = S.sth; p[8 * cap] = S.Ax; p[9 * cap] = S.Ay; p[10 * cap] = S.h_abs;
+    p[11 * cap] = S.t; p[12 * cap] = lx; p[13 * cap] = ly; p[14 * cap] = rejected ? 1.0 : 0.0;
+}
+
+template <class TR>
+__device__ __forceinline__ void save_event(const DevCfg& c, uint32_t slot, long long i, const Integ<TR>& S, double h,
+                                           const double (&Ax)[7], const double (&Ay)[7], uint32_t active, double lx,
+                                           double ly) {
+    const long long cap = c.q_cap;
+    double* p = c.scr_event + slot;
+    c.q_event[slot] = (uint32_t)i;
+    p[0 * cap] = S.x; p[1 * cap] = S.y; p[2 * cap] = S.th; p[3 * cap] = S.vx; p[4 * cap] = S.vy; p[5 * cap] = S.om;
+    p[6 * cap] = h; p[7 * cap] = S.t;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        p[(8 + k) * cap] = Ax[k];
+        p[(15 + k) * cap] = Ay[k];
+    }
+    p[22 * cap] = lx; p[23 * cap] = ly; p[24 * cap] = (double)active;
+}
+
+enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2 };
+
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock)
+hot_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long long step0, OT* __restrict__ obs,
+           double* __restrict__ reward, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    constexpr int D = TR::D;
+    __shared__ __align__(16) OT sobs[kBlock * D];
+    const long long block_first = (long long)blockIdx.x * kBlock;
+    const long long i = block_first + threadIdx.x;
+    const bool valid = i < c.n;
+    double st[4] = {0, 0, 0, 0};
+    int kind = KIND_DONE;
+    bool need_post = false, reached = false, done = false, rejected = false;
+    Integ<TR> S;
+    double Ax[7], Ay[7], h = 0, lx = 0, ly = 0;
+    uint32_t active = 0;
+
+    if (valid) {
+        EnvRegs<TR> e;
+        load_env<TR>(c, i, e);
+        const Act act = fetch_action<TR>(c, actions, i, step0);
+        lx = e.x;
+        ly = e.y;  // env.last_xy (spaceship_env.py:74)
+        double g[TR::NEV], pd[TR::NP];
+        init_step<TR>(c, e, act, S, g, pd);
+        // first _step_impl attempt (scipy:rk.py:111-143); t = 0
+        double t_new = S.h_abs;
+        if (t_new - c.T > 0) t_new = c.T;
+        h = t_new;
+        S.h_abs = fabs(h);
+        double xn, yn, thn, vxn, vyn, omn, cn, sn, err;
+        rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err);
+        if (!controller(err, rejected, t_new < c.T, S.h_abs)) {
+            kind = KIND_CONT;  // rejected: the attempt loop is resumed from the same state with the smaller step
+        } else {
+            double gn[TR::NEV];
+            event_values(c, e, xn, yn, omn, gn, pd);
+            active = active_events<TR>(g, gn);
+            if (active) {
+                kind = KIND_EVENT;
+            } else if (t_new < c.T) {
+                kind = KIND_CONT;
+                S.x = xn; S.y = yn; S.th = thn; S.vx = vxn; S.vy = vyn; S.om = omn;
+                S.cth = cn; S.sth = sn; S.Ax = Ax[6]; S.Ay = Ay[6]; S.t = t_new;
+            } else {
+                uint32_t status = 0;
+                commit_state<TR>(e, xn, yn, thn, vxn, vyn, omn, status);
+                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, false, obs ? sobs + threadIdx.x * D : nullptr, cn, sn,
+                                   reward, done_out, trunc_out, st, reached, done);
+                need_post = reached || (done && c.auto_reset);
+                if (status) c.status[i] |= status;
+            }
+        }
+    }
+    // queue appends at warp-converged points
+    const uint32_t s_cont = queue_push(&c.q_counts[0], kind == KIND_CONT);
+    const uint32_t s_event = queue_push(&c.q_counts[1], kind == KIND_EVENT);
+    const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
+    if (kind == KIND_CONT) save_cont<TR>(c, s_cont, i, S, lx, ly, rejected);
+    if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
+    if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
+    if (obs) {
+        __syncthreads();
+        flush_obs<OT, D>(sobs, obs, block_first, c.n);  // rows of queued envs are rewritten by the later kernels
+    }
+    block_stats_flush<kBlock>(c, st);
+}
+
+// envs that need more than one Runge-Kutta step: resume solve_ivp's loop, densely packed
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock)
+cont_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long long step0, OT* __restrict__ obs,
+            double* __restrict__ reward, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    const uint32_t count = c.q_counts[0];
+    const long long cap = c.q_cap;
+    double st[4] = {0, 0, 0, 0};
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+        const uint32_t j = base + threadIdx.x;
+        const bool valid = j < count;
+        bool is_event = false, need_post = false, reached = false, done = false;
+        long long i = 0;
+        Integ<TR> S;
+        EventIO<TR> io;
+        double lx = 0, ly = 0;
+        if (valid) {
+            i = c.q_cont[j];
+            EnvRegs<TR> e;
+            load_env<TR>(c, i, e);
+            const Act act = fetch_action<TR>(c, actions, i, step0);
+            const double* p = c.scr_cont + j;
+            S.x = p[0 * cap]; S.y = p[1 * cap]; S.th = p[2 * cap]; S.vx = p[3 * cap]; S.vy = p[4 * cap];
+            S.om = p[5 * cap]; S.cth = p[6 * cap]; S.sth = p[7 * cap]; S.Ax = p[8 * cap]; S.Ay = p[9 * cap];
+            S.h_abs = p[10 * cap]; S.t = p[11 * cap];
+            lx = p[12 * cap]; ly = p[13 * cap];
+            const bool rejected = p[14 * cap] != 0.0;
+            S.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
+            S.fs = act.fs;
+            double g[TR::NEV], pd[TR::NP];
+            event_values(c, e, S.x, S.y, S.om, g, pd);
+            const int rc = rk_loop<TR>(c, e, S, g, rejected, &io, pd);
+            if (rc == RK_EVENT) {
+                is_event = true;
+            } else {
+                uint32_t status = (rc == RK_FAILED) ? 1u : 0u;
+                commit_state<TR>(e, S.x, S.y, S.th, S.vx, S.vy, S.om, status);
+                OT row[TR::D];
+                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, false, obs ? row : nullptr, S.cth, S.sth, reward, done_out,
+                                   trunc_out, st, reached, done);
+                if (obs) {
+#pragma unroll
+                    for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
+                }
+                need_post = reached || (done && c.auto_reset);
+                if (status) c.status[i] |= status;
+            }
+        }
+        const uint32_t s_event = queue_push(&c.q_counts[1], is_event);
+        const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
+        if (is_event) {
+            Integ<TR> So;
+            So.x = io.x; So.y = io.y; So.th = io.th; So.vx = io.vx; So.vy = io.vy; So.om = io.om; So.t = io.t_old;
+            save_event<TR>(c, s_event, i, So, io.h, io.Ax, io.Ay, io.active, lx, ly);
+        }
+        if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
+    }
+    block_stats_flush<kBlock>(c, st);
+}
+
+// terminal events (dense output + Brent roots + epilogue + reset) and the post work of finished envs
+constexpr int kTailBlock = 64;
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kTailBlock)
+tail_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long long step0, OT* __restrict__ obs,
+            double* __restrict__ reward, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    const uint32_t n_event = c.q_counts[1], n_post = c.q_counts[2];
+    const uint32_t total = n_event + n_post;
+    const long long cap = c.q_cap;
+    double st[4] = {0, 0, 0, 0};
+    for (uint32_t base = blockIdx.x * kTailBlock; base < total; base += gridDim.x * kTailBlock) {
+        const uint32_t j = base + threadIdx.x;
+        if (j < n_event) {
+            const long long i = c.q_event[j];
+            EnvRegs<TR> e;
+            load_env<TR>(c, i, e);
+            const Act act = fetch_action<TR>(c, actions, i, step0);
+            const double* p = c.scr_event + j;
+            EventIO<TR> io;
+            io.x = p[0 * cap]; io.y = p[1 * cap]; io.th = p[2 * cap]; io.vx = p[3 * cap]; io.vy = p[4 * cap];
+            io.om = p[5 * cap]; io.h = p[6 * cap]; io.t_old = p[7 * cap];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                io.Ax[k] = p[(8 + k) * cap];
+                io.Ay[k] = p[(15 + k) * cap];
+            }
+            const double lx = p[22 * cap], ly = p[23 * cap];
+            io.active = (uint32_t)p[24 * cap];
+            io.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
+#pragma unroll
+            for (int q = 0; q < TR::NP; ++q) {
+                io.px[q] = e.px[q];
+                io.py[q] = e.py[q];
+            }
+            handle_events<TR>(c, &io);
+            uint32_t status = io.status;
+            commit_state<TR>(e, io.x, io.y, io.th, io.vx, io.vy, io.om, status);
+            double gd[TR::NEV], pd[TR::NP];
+            event_values(c, e, e.x, e.y, e.om, gd, pd);
+            double sn, cs;
+            sincos(e.th, &sn, &cs);
+            OT row[TR::D];
+            const bool want_row = obs && !c.auto_reset;  // with auto-reset the reset observation replaces it
+            bool reached, done;
+            finish_env<TR, OT>(c, i, e, act, lx, ly, pd, true, want_row ? row : nullptr, cs, sn, reward, done_out,
+                               trunc_out, st, reached, done);
+            if (want_row) {
+#pragma unroll
+                for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
+            }
+            if (status) c.status[i] |= status;
+            post_env<TR, OT>(c, i, reached, done, obs);
+        } else if (j < total) {
+            const uint32_t w = c.q_post[j - n_event];
+            post_env<TR, OT>(c, (long long)(w & kPostIndex), (w & kPostReached) != 0, (w & kPostDone) != 0, obs);
+        }
+    }
+    block_stats_flush<kTailBlock>(c, st);
+    // the last block to finish empties the queues for the next step
+    __shared__ bool last;
+    __threadfence();
+    if (threadIdx.x == 0) last = (atomicAdd(&c.q_counts[3], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x < 4) c.q_counts[threadIdx.x] = 0;
+}
+
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock)
 reset_kernel(const DevCfg c, const uint8_t* __restrict__ mask, OT* __restrict__ obs) {
@@ -331,12 +690,13 @@ struct sg_env {
     sg_config cfg;
     sg_layout lay;
     DevCfg dev;
-    int device;
+    int device, sm_count;
     uint64_t seed;
     int64_t n, first_env;
     void* state;
     bool owns_state;
     double* d_stats;
+    void* d_queues;  // work queues + scratch of the split step path
     uint64_t step_count;
     int64_t launches;
     std::string err;
@@ -533,6 +893,17 @@ static void build_dev(sg_env* h) {
     d.rng_ctr = (uint32_t*)(base + h->lay.rng_ctr);
     d.status = (uint32_t*)(base + h->lay.status);
     d.stats = h->d_stats;
+    {   // queue block: counts (256 B) | cont idx | event idx | post idx | cont scratch | event scratch
+        char* q = (char*)h->d_queues;
+        const size_t n = (size_t)h->n, idx_bytes = ((n * 4 + 255) / 256) * 256;
+        d.q_counts = (uint32_t*)q;
+        d.q_cont = (uint32_t*)(q + 256);
+        d.q_event = (uint32_t*)(q + 256 + idx_bytes);
+        d.q_post = (uint32_t*)(q + 256 + 2 * idx_bytes);
+        d.scr_cont = (double*)(q + 256 + 3 * idx_bytes);
+        d.scr_event = d.scr_cont + (size_t)kContFields * n;
+        d.q_cap = h->n;
+    }
     d.n = h->n;
     d.first_env = h->first_env;
     d.seed = h->seed;
@@ -584,6 +955,7 @@ static void build_dev(sg_env* h) {
 extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint64_t seed, int64_t first_env_index,
                          void* d_state, sg_env** out) {
     if (!cfg || !out || n_envs <= 0) return fail(nullptr, SG_ERR_INVALID, "sg_create: bad arguments");
+    if (n_envs >= (1ll << 30)) return fail(nullptr, SG_ERR_INVALID, "sg_create: at most 2^30 - 1 envs per handle");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, SG_ERR_NO_DEVICE, "sg_create: no CUDA device (this library has no CPU path)");
@@ -592,6 +964,8 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     if (sg_config_finalize(&c) != SG_OK) return fail(nullptr, SG_ERR_INVALID, "sg_create: unsupported configuration");
     SG_CUDA(nullptr, cudaSetDevice(device));
     sg_env* h = new sg_env();
+    h->sm_count = 148;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     h->cfg = c;
     h->device = device;
     h->seed = seed;
@@ -599,6 +973,8 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     h->first_env = first_env_index;
     h->step_count = 0;
     h->launches = 0;
+    h->d_queues = nullptr;
+    h->d_stats = nullptr;
     h->hstream = nullptr;
     h->s_actions = nullptr;
     h->s_actions_bytes = 0;
@@ -612,6 +988,10 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     cudaError_t err = cudaSuccess;
     if (h->owns_state) err = cudaMalloc(&h->state, (size_t)h->lay.total_bytes);
     if (err == cudaSuccess) err = cudaMalloc((void**)&h->d_stats, 4 * sizeof(double));
+    const size_t q_bytes = 256 + 3 * ((((size_t)n_envs * 4 + 255) / 256) * 256) +
+                           (size_t)(kContFields + kEventFields) * (size_t)n_envs * sizeof(double);
+    if (err == cudaSuccess) err = cudaMalloc(&h->d_queues, q_bytes);
+    if (err == cudaSuccess) err = cudaMemset(h->d_queues, 0, 256);
     if (err == cudaSuccess) err = cudaMemset(h->state, 0, (size_t)h->lay.total_bytes);
     if (err == cudaSuccess) err = cudaMemset(h->d_stats, 0, 4 * sizeof(double));
     if (err != cudaSuccess) {
@@ -640,6 +1020,7 @@ extern "C" void sg_destroy(sg_env* h) {
     cudaSetDevice(h->device);
     if (h->owns_state && h->state) cudaFree(h->state);
     if (h->d_stats) cudaFree(h->d_stats);
+    if (h->d_queues) cudaFree(h->d_queues);
     if (h->s_actions) cudaFree(h->s_actions);
     if (h->s_obs) cudaFree(h->s_obs);
     if (h->s_reward) cudaFree(h->s_reward);
@@ -664,7 +1045,7 @@ extern "C" int sg_set_step_count(sg_env* h, uint64_t s) {
 extern "C" int64_t sg_kernel_launches(const sg_env* h) { return h ? h->launches : 0; }
 
 // ---- kernel dispatch over (task, planets, steering, action space, obs dtype) -------------------
-enum Op { OP_STEP, OP_RESET, OP_VFIELD };
+enum Op { OP_STEP, OP_STEP_SPLIT, OP_RESET, OP_VFIELD };
 
 struct LaunchArgs {
     Op op;
@@ -683,10 +1064,20 @@ struct LaunchArgs {
 template <class TR, typename OT>
 static void launch_typed(const sg_env* h, const LaunchArgs& a) {
     const int blocks = (int)((h->n + kBlock - 1) / kBlock);
-    if (a.op == OP_STEP)
+    if (a.op == OP_STEP) {
         step_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.K, a.step0, (OT*)a.obs, a.reward, a.done,
                                                              a.trunc);
-    else if (a.op == OP_RESET)
+    } else if (a.op == OP_STEP_SPLIT) {
+        const int sms = h->sm_count > 0 ? h->sm_count : 148;
+        const int cont_blocks = blocks < sms * 8 ? blocks : sms * 8;
+        const long long tb = (h->n + kTailBlock - 1) / kTailBlock;
+        const int tail_blocks = (int)(tb < sms * 8 ? tb : sms * 8);
+        hot_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.step0, (OT*)a.obs, a.reward, a.done, a.trunc);
+        cont_kernel<TR, OT><<<cont_blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.step0, (OT*)a.obs, a.reward, a.done,
+                                                                  a.trunc);
+        tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, a.stream>>>(h->dev, a.actions, a.step0, (OT*)a.obs, a.reward,
+                                                                      a.done, a.trunc);
+    } else if (a.op == OP_RESET)
         reset_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.mask, (OT*)a.obs);
 }
 
@@ -718,7 +1109,7 @@ static int launch(sg_env* h, const LaunchArgs& a) {
     else if (h->cfg.n_planets == 3) launch_np<TASK_GOAL, 3>(h, a);
     else if (h->cfg.n_planets == 4) launch_np<TASK_GOAL, 4>(h, a);
     else return fail(h, SG_ERR_INVALID, "unsupported n_planets");
-    h->launches += 1;
+    h->launches += (a.op == OP_STEP_SPLIT) ? 3 : 1;
     SG_CUDA(h, cudaGetLastError());
     return SG_OK;
 }
@@ -740,19 +1131,39 @@ extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, do
     if (!h || K <= 0) return SG_ERR_INVALID;
     if (d_obs && !aligned16(d_obs)) return fail(h, SG_ERR_INVALID, "sg_step: d_obs must be 16-byte aligned");
     if (d_actions && (((uintptr_t)d_actions) & 7u)) return fail(h, SG_ERR_INVALID, "sg_step: d_actions must be 8-byte aligned");
+    const int mode = h->cfg.step_mode;
+    const bool split = (mode == SG_STEP_SPLIT) || (mode == SG_STEP_AUTO && K == 1);
     LaunchArgs a{};
-    a.op = OP_STEP;
     a.stream = (cudaStream_t)stream;
-    a.actions = d_actions;
-    a.K = K;
-    a.step0 = h->step_count;
-    a.obs = d_obs;
-    a.reward = d_reward;
-    a.done = d_done;
-    a.trunc = d_truncated;
-    int rc = launch(h, a);
-    if (rc == SG_OK) h->step_count += (uint64_t)K;
-    return rc;
+    if (!split) {
+        a.op = OP_STEP;
+        a.actions = d_actions;
+        a.K = K;
+        a.step0 = h->step_count;
+        a.obs = d_obs;
+        a.reward = d_reward;
+        a.done = d_done;
+        a.trunc = d_truncated;
+        int rc = launch(h, a);
+        if (rc == SG_OK) h->step_count += (uint64_t)K;
+        return rc;
+    }
+    // split path: K single steps, three launches each; the observation is only needed after the last one
+    a.op = OP_STEP_SPLIT;
+    a.K = 1;
+    for (int k = 0; k < K; ++k) {
+        const size_t off = (size_t)k * (size_t)h->n;
+        a.actions = d_actions ? d_actions + 2 * off : nullptr;
+        a.step0 = h->step_count;
+        a.obs = (k == K - 1) ? d_obs : nullptr;
+        a.reward = d_reward ? d_reward + off : nullptr;
+        a.done = d_done ? d_done + off : nullptr;
+        a.trunc = d_truncated ? d_truncated + off : nullptr;
+        int rc = launch(h, a);
+        if (rc != SG_OK) return rc;
+        h->step_count += 1;
+    }
+    return SG_OK;
 }
 
 extern "C" int sg_vector_field(sg_env* h, const float* d_actions, double* d_out, void* stream) {

@@ -30,7 +30,7 @@ _KEPLER_KW = {
 }
 # engine-level options (not in the reference constructors)
 _ENGINE_KW = {"max_episode_steps": "max_episode_steps", "auto_reset": "auto_reset", "discrete": "discrete",
-              "obs_dtype": "obs_dtype"}
+              "obs_dtype": "obs_dtype", "step_mode": "step_mode"}
 
 
 def make_config(env_id, **kwargs):
@@ -49,6 +49,8 @@ def make_config(env_id, **kwargs):
             continue
         if k == "obs_dtype":
             v = {"float64": 0, "float32": 1, 0: 0, 1: 1}[str(v).replace("torch.", "") if not isinstance(v, int) else v]
+        if k == "step_mode":
+            v = {"auto": 0, "fused": 1, "split": 2, 0: 0, 1: 1, 2: 2}[v]
         if k == "ship_steering":
             v = int(getattr(v, "value", v))
             if v not in (0, 1):

@@ -23,8 +23,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_sg_config_struct_matches_header_size():
-    # 8 int32 + 22 double + 2 int32 + 7 double
-    assert C.sizeof(SgConfig) == 8 * 4 + 22 * 8 + 2 * 4 + 7 * 8
+    # 10 int32 + 22 double + 2 int32 + 7 double
+    assert C.sizeof(SgConfig) == 10 * 4 + 22 * 8 + 2 * 4 + 7 * 8
     assert C.sizeof(SgLayout) == 13 * 8
 
 

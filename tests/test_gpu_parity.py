@@ -21,12 +21,13 @@ def _make(case, n, seed=0, **extra):
     return sg.make(env_id, n, seed=seed, **kw)
 
 
+@pytest.mark.parametrize("mode", ["split", "fused"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_transitions_match_reference_golden(case):
+def test_transitions_match_reference_golden(case, mode):
     """Identical (state, action) pairs harvested from the reference -> same next state, obs, reward, flags."""
     g = load("transitions", case)
     n = len(g["reward"])
-    env = _make(case, n, auto_reset=0, max_episode_steps=0)
+    env = _make(case, n, auto_reset=0, max_episode_steps=0, step_mode=mode)
     st = {"ship": g["state0"]}
     if env.cfg.task == 0:
         st["planets"] = g["planets"].reshape(n, -1)
@@ -47,15 +48,20 @@ def test_transitions_match_reference_golden(case):
     env.close()
 
 
-@pytest.mark.parametrize("case", ["goal2p", "goal3p", "goal4p", "goal3p_accel", "kepler_circle",
-                                  "kepler_hard_accel_rand", "goal3p_discrete", "kepler_discrete"])
-def test_rollout_lockstep_with_oracle_engine(oracle, case):
-    """Whole engine (auto-reset, TimeLimit, Philox streams, goal resampling) in lockstep with the CPU twin."""
+LOCKSTEP = [(c, "split") for c in ("goal2p", "goal3p", "goal4p", "goal3p_accel", "kepler_circle",
+                                    "kepler_hard_accel_rand", "goal3p_discrete", "kepler_discrete")]
+LOCKSTEP += [(c, "fused") for c in ("goal3p", "goal2p", "kepler_hard_accel_rand", "goal3p_discrete")]
+
+
+@pytest.mark.parametrize("case,mode", LOCKSTEP)
+def test_rollout_lockstep_with_oracle_engine(oracle, case, mode):
+    """Whole engine (auto-reset, TimeLimit, Philox streams, goal resampling) in lockstep with the CPU twin,
+    through the split kernels (hot/continuation/tail + work queues) and through the fused kernel."""
     n, T, seed, first = 2048, 160, 1234, 7_000_000_000
     cfg = oracle_cfg(oracle, case, max_episode_steps=60)
     eng = oracle.Engine(cfg, n, seed=seed, first_env_index=first)
     env_id, kw = engine_kwargs(case)
-    env = sg.make(env_id, n, seed=seed, first_env_index=first, max_episode_steps=60, **kw)
+    env = sg.make(env_id, n, seed=seed, first_env_index=first, max_episode_steps=60, step_mode=mode, **kw)
     obs_o = eng.reset()
     obs_d = env.reset()
     assert close(obs_d.cpu().numpy(), obs_o).all()
@@ -81,7 +87,9 @@ def test_rollout_lockstep_with_oracle_engine(oracle, case):
 
 @pytest.mark.parametrize("case", ["goal3p", "kepler_random"])
 def test_fused_substeps_and_synthetic_actions(oracle, case):
-    """K fused substeps with in-kernel random actions == K single launches == the oracle twin."""
+    """K fused substeps (one launch, state in registers) with in-kernel random actions == K single steps
+    through the split kernels == the oracle twin.  The two GPU paths share their device functions but are
+    compiled into different kernels (different FMA contraction), so they are compared to the parity bar."""
     n, K, seed = 4096, 12, 99
     cfg = oracle_cfg(oracle, case, max_episode_steps=40)
     env_id, kw = engine_kwargs(case)
@@ -91,23 +99,24 @@ def test_fused_substeps_and_synthetic_actions(oracle, case):
     a.reset(); b.reset(); eng.reset()
     for rep in range(3):
         oa, ra, da, _ = a.step_many(K=K)
+        rb, db = [], []
         for k in range(K):
-            ob, rb, db, _ = b.step_many(K=1)
-            assert torch.equal(ra[k], rb[0]) and torch.equal(da[k], db[0])
-        assert torch.equal(oa, ob)
-        sa, sb = a.get_state(), b.get_state()
-        for key in sa:
-            if key != "step_count":
-                assert torch.equal(sa[key], sb[key]), key
+            ob, r1, d1, _ = b.step_many(K=1)
+            rb.append(r1[0]); db.append(d1[0])
+        rb, db = torch.stack(rb), torch.stack(db)
         oo, ro, do, _ = eng.step(None, K=K)
-        ok = close(oa.cpu().numpy(), oo).all(axis=1) & close(ra.cpu().numpy(), ro).all(axis=0)
-        ok &= (da.cpu().numpy() == do.astype(bool)).all(axis=0)
-        assert (~ok).sum() <= 1
-        if (~ok).any():
-            a.set_state(oracle_state_to_engine(cfg, eng.envs)); b.set_state(oracle_state_to_engine(cfg, eng.envs))
+        for o_, r_, d_ in ((oa, ra, da), (ob, rb, db)):
+            ok = close(o_.cpu().numpy(), oo).all(axis=1) & close(r_.cpu().numpy(), ro).all(axis=0)
+            ok &= (d_.cpu().numpy() == do.astype(bool)).all(axis=0)
+            assert (~ok).sum() <= 1
+        for env in (a, b):
+            ok = compare_engine_to_oracle(cfg, env.get_state(), eng.envs)
+            assert (~ok).sum() <= 1
+            if (~ok).any():
+                env.set_state(oracle_state_to_engine(cfg, eng.envs))
     sa, sb = a.stats(), b.stats()
-    assert sa["episodes"] == sb["episodes"] and sa["goals"] == sb["goals"] and sa["length_sum"] == sb["length_sum"]
-    assert abs(sa["return_sum"] - sb["return_sum"]) <= 1e-9 * max(1.0, abs(sa["return_sum"]))
+    assert abs(sa["episodes"] - sb["episodes"]) <= 2 and abs(sa["goals"] - sb["goals"]) <= 2
+    assert abs(sa["episodes"] - eng.stats[2]) <= 2 and sa["episodes"] > n / 2
     a.close(); b.close()
 
 
