@@ -32,6 +32,36 @@ constexpr double kRtol = 1e-3, kAtol = 1e-6;  // solve_ivp defaults
 constexpr double kEps = 2.220446049250313e-16;
 constexpr double kInvSqrt6 = 0.40824829046386301637;
 
+// ---- branch-free FP64 reciprocal / rsqrt / sqrt / divide --------------------------------------------
+// The CUDA math library versions carry a slow-path CALL for denormal / infinite operands (argument
+// marshalling, BSSY/BSYNC, register moves).  The operands here are ordinary normal numbers (distances,
+// tolerances, norms), so the hardware approximation (MUFU.RCP64H / RSQ64H, ~2^-22) plus one cubically
+// convergent correction gives <= 1-2 ulp without any branch.  None of these feed the float32 roundings
+// of the action path (those keep the exact __f*_rn intrinsics).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);  // y (1 + e + e^2)
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);  // 1 - x y^2
+    return fma(y * e, fma(e, 0.375, 0.5), y);  // y (1 + e/2 + 3 e^2 / 8)
+}
+__device__ __forceinline__ double fast_sqrt(double x) {  // x > 0 (x == 0 handled by the caller where possible)
+    const double y = fast_rsqrt(x);
+    const double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);  // one Newton step on s: removes the rounding of x * y
+}
+__device__ __forceinline__ double fast_sqrt0(double x) { return x > 0.0 ? fast_sqrt(x) : 0.0; }
+__device__ __forceinline__ double fast_div(double a, double b) {
+    const double y = fast_rcp(b);
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);  // residual correction
+}
+
 enum { TASK_GOAL = 0, TASK_KEPLER = 1 };
 enum { STEER_ACC = 0, STEER_VEL = 1 };
 
@@ -93,14 +123,15 @@ struct DevCfg {
     uint32_t* status;
     double* stats;  // 4 doubles: sum return, sum length, episodes, goals
     // work queues of the split step path (library-owned scratch, empty between sg_step calls)
-    uint32_t* q_counts;   // [0] continuation, [1] event, [2] post, [3] block ticket
+    uint32_t* q_counts;   // [0] continuation, [1] event, [2] post, [3] block ticket, [4..5] u64 step counter
     uint32_t* q_cont;     // env indices
     uint32_t* q_event;
     uint32_t* q_post;     // env index | reached << 30 | done << 31
     double* scr_cont;     // [13][cap]: x y th vx vy om cth sth Ax Ay h_abs t flags(lx, ly separately)
     double* scr_event;    // [24][cap]
     long long q_cap;
-    long long n;
+    long long n;       // envs of this (sub-)batch
+    long long stride;  // field stride of the struct-of-arrays state = envs of the whole handle
     long long first_env;
     unsigned long long seed;
     int max_episode_steps, randomize, auto_reset, rows, cols;
@@ -262,7 +293,7 @@ __device__ __forceinline__ void accel(const DevCfg& c, const EnvRegs<TR>& e, dou
 #pragma unroll
     for (int p = 0; p < TR::NP; ++p) {
         double dx = e.px[p] - x, dy = e.py[p] - y;
-        double inv = rsqrt(dx * dx + dy * dy);
+        double inv = fast_rsqrt(dx * dx + dy * dy);
         double s = c.gm0 * (inv * inv * inv);
         fx = fma(dx, s, fx);
         fy = fma(dy, s, fy);
@@ -279,7 +310,7 @@ __device__ __forceinline__ void event_values(const DevCfg& c, const EnvRegs<TR>&
 #pragma unroll
     for (int p = 0; p < TR::NP; ++p) {
         double dx = e.px[p] - x, dy = e.py[p] - y;
-        pd[p] = sqrt(dx * dx + dy * dy);
+        pd[p] = fast_sqrt(dx * dx + dy * dy);
     }
     if (TR::TASK == TASK_GOAL) {
 #pragma unroll
@@ -507,9 +538,9 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     sincos(S.th, &S.sth, &S.cth);
     accel(c, e, S.x, S.y, S.cth, S.sth, S.fs, S.Ax, S.Ay);  // f0
     const double x = S.x, y = S.y, th = S.th, vx = S.vx, vy = S.vy, om = S.om, alpha = S.alpha;
-    double rx = 1.0 / (kAtol + fabs(x) * kRtol), ry = 1.0 / (kAtol + fabs(y) * kRtol);
-    double rth = 1.0 / (kAtol + fabs(th) * kRtol), rvx = 1.0 / (kAtol + fabs(vx) * kRtol);
-    double rvy = 1.0 / (kAtol + fabs(vy) * kRtol), rom = 1.0 / (kAtol + fabs(om) * kRtol);
+    double rx = fast_rcp(kAtol + fabs(x) * kRtol), ry = fast_rcp(kAtol + fabs(y) * kRtol);
+    double rth = fast_rcp(kAtol + fabs(th) * kRtol), rvx = fast_rcp(kAtol + fabs(vx) * kRtol);
+    double rvy = fast_rcp(kAtol + fabs(vy) * kRtol), rom = fast_rcp(kAtol + fabs(om) * kRtol);
     double q, S0 = 0, S1 = 0, S2 = 0;
     q = x * rx; S0 = fma(q, q, S0);
     q = y * ry; S0 = fma(q, q, S0);
@@ -523,8 +554,8 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     q = S.Ax * rvx; S1 = fma(q, q, S1);
     q = S.Ay * rvy; S1 = fma(q, q, S1);
     q = alpha * rom; S1 = fma(q, q, S1);
-    double d0 = sqrt(S0) * kInvSqrt6, d1 = sqrt(S1) * kInvSqrt6;
-    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    double d0 = fast_sqrt0(S0) * kInvSqrt6, d1 = fast_sqrt0(S1) * kInvSqrt6;
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : fast_div(0.01 * d0, d1);
     h0 = fmin(h0, T);
     double Bx, By, cn, sn;
     const double dprobe = h0 * om;
@@ -534,7 +565,7 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     q = h0 * alpha * rth; S2 = fma(q, q, S2);
     q = (Bx - S.Ax) * rvx; S2 = fma(q, q, S2);
     q = (By - S.Ay) * rvy; S2 = fma(q, q, S2);
-    double d2 = sqrt(S2) * kInvSqrt6 / h0;
+    double d2 = fast_div(fast_sqrt0(S2) * kInvSqrt6, h0);
     const double dm = fmax(d1, d2);
     const double lim = fmin(100 * h0, T);
     double h_abs;
@@ -545,14 +576,63 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
         // (x -> x^5 is monotone), and pay for pow only on the lanes that need its value.
         const double l2 = lim * lim;
         if (0.01 >= dm * (l2 * l2 * lim) * 1.0000000001) h_abs = lim;
-        else h_abs = fmin(lim, pow(0.01 / dm, 0.2));
+        else h_abs = fmin(lim, pow(fast_div(0.01, dm), 0.2));
     }
     S.h_abs = h_abs;
     event_values(c, e, x, y, om, g, pd);
 }
 
+struct SinCos6 {
+    double s[6], c[6];
+};
+__device__ __noinline__ SinCos6 slow_sincos6(double d0, double d1, double d2, double d3, double d4, double d5) {
+    SinCos6 r;
+    const double d[6] = {d0, d1, d2, d3, d4, d5};
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) sincos(d[j], &r.s[j], &r.c[j]);
+    return r;
+}
+
+// cos / sin of N small heading increments at once: the Horner chains are interleaved (N-way ILP) and every
+// Taylor coefficient is materialised once for all N.
+template <int N>
+__device__ __forceinline__ void small_sincos_n(const double (&d)[N], bool small, double (&sn)[N], double (&cs)[N]) {
+    if (small) {
+        double d2[N], ps[N], pc[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            d2[j] = d[j] * d[j];
+            ps[j] = fma(d2[j], 1.0 / 6227020800.0, -1.0 / 39916800.0);
+            pc[j] = fma(d2[j], -1.0 / 87178291200.0, 1.0 / 479001600.0);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], 1.0 / 362880.0); pc[j] = fma(pc[j], d2[j], -1.0 / 3628800.0); }
+#pragma unroll
+        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], -1.0 / 5040.0); pc[j] = fma(pc[j], d2[j], 1.0 / 40320.0); }
+#pragma unroll
+        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], 1.0 / 120.0); pc[j] = fma(pc[j], d2[j], -1.0 / 720.0); }
+#pragma unroll
+        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], -1.0 / 6.0); pc[j] = fma(pc[j], d2[j], 1.0 / 24.0); }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            sn[j] = fma(ps[j] * d2[j], d[j], d[j]);
+            pc[j] = fma(pc[j], d2[j], -0.5);
+            cs[j] = fma(pc[j], d2[j], 1.0);
+        }
+    } else {  // |increment| >= 0.5 rad: only states injected from outside (|omega| > omega_max)
+        static_assert(N == 6, "slow path is written for the six stage headings");
+        const SinCos6 r = slow_sincos6(d[0], d[1], d[2], d[3], d[4], d[5]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            sn[j] = r.s[j];
+            cs[j] = r.c[j];
+        }
+    }
+}
+
 // One Runge-Kutta attempt of size h from S (rk_step, scipy:rk.py:14-71) in Nystrom form, plus the error
-// norm (scipy:rk.py:105-109,141-143; the heading rows integrate exactly and contribute 0).
+// norm (scipy:rk.py:105-109,141-143; the heading rows integrate exactly and contribute 0).  The six stage
+// headings depend only on (h, omega, alpha), so their cos / sin are computed up front, together.
 template <class TR>
 __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e, const Integ<TR>& S, double h,
                                            double (&Ax)[7], double (&Ay)[7], double& xn, double& yn, double& thn,
@@ -561,36 +641,50 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     const double x = S.x, y = S.y, vx = S.vx, vy = S.vy;
     const double hh = h * h, ho = h * S.om, ha = hh * S.alpha;
     const bool small = fabs(ho) + fabs(ha) < 0.5;
+    double d[6], sd[6], cd[6];
+    d[0] = c2 * ho;
+    d[1] = c3 * ho + cs3 * ha;
+    d[2] = c4 * ho + cs4 * ha;
+    d[3] = c5 * ho + cs5 * ha;
+    d[4] = ho + cs6 * ha;
+    d[5] = ho + cs7 * ha;
+    small_sincos_n<6>(d, small, sd, cd);
+    double cr[6], sr[6];  // stage headings: the base heading rotated by d[j]
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        cr[j] = S.cth * cd[j] - S.sth * sd[j];
+        sr[j] = S.sth * cd[j] + S.cth * sd[j];
+    }
     Ax[0] = S.Ax;
     Ay[0] = S.Ay;
-    accel_rot(c, e, S, x + (c2 * h) * vx, y + (c2 * h) * vy, c2 * ho, small, Ax[1], Ay[1], cn, sn);
-    accel_rot(c, e, S, x + (c3 * h) * vx + hh * (ab31 * Ax[0]), y + (c3 * h) * vy + hh * (ab31 * Ay[0]),
-              c3 * ho + cs3 * ha, small, Ax[2], Ay[2], cn, sn);
-    accel_rot(c, e, S, x + (c4 * h) * vx + hh * (ab41 * Ax[0] + ab42 * Ax[1]),
-              y + (c4 * h) * vy + hh * (ab41 * Ay[0] + ab42 * Ay[1]), c4 * ho + cs4 * ha, small, Ax[3], Ay[3], cn, sn);
-    accel_rot(c, e, S, x + (c5 * h) * vx + hh * (ab51 * Ax[0] + ab52 * Ax[1] + ab53 * Ax[2]),
-              y + (c5 * h) * vy + hh * (ab51 * Ay[0] + ab52 * Ay[1] + ab53 * Ay[2]), c5 * ho + cs5 * ha, small, Ax[4],
-              Ay[4], cn, sn);
-    accel_rot(c, e, S, x + h * vx + hh * (ab61 * Ax[0] + ab62 * Ax[1] + ab63 * Ax[2] + ab64 * Ax[3]),
-              y + h * vy + hh * (ab61 * Ay[0] + ab62 * Ay[1] + ab63 * Ay[2] + ab64 * Ay[3]), ho + cs6 * ha, small,
-              Ax[5], Ay[5], cn, sn);
+    accel(c, e, x + (c2 * h) * vx, y + (c2 * h) * vy, cr[0], sr[0], S.fs, Ax[1], Ay[1]);
+    accel(c, e, x + (c3 * h) * vx + hh * (ab31 * Ax[0]), y + (c3 * h) * vy + hh * (ab31 * Ay[0]), cr[1], sr[1], S.fs,
+          Ax[2], Ay[2]);
+    accel(c, e, x + (c4 * h) * vx + hh * (ab41 * Ax[0] + ab42 * Ax[1]),
+          y + (c4 * h) * vy + hh * (ab41 * Ay[0] + ab42 * Ay[1]), cr[2], sr[2], S.fs, Ax[3], Ay[3]);
+    accel(c, e, x + (c5 * h) * vx + hh * (ab51 * Ax[0] + ab52 * Ax[1] + ab53 * Ax[2]),
+          y + (c5 * h) * vy + hh * (ab51 * Ay[0] + ab52 * Ay[1] + ab53 * Ay[2]), cr[3], sr[3], S.fs, Ax[4], Ay[4]);
+    accel(c, e, x + h * vx + hh * (ab61 * Ax[0] + ab62 * Ax[1] + ab63 * Ax[2] + ab64 * Ax[3]),
+          y + h * vy + hh * (ab61 * Ay[0] + ab62 * Ay[1] + ab63 * Ay[2] + ab64 * Ay[3]), cr[4], sr[4], S.fs, Ax[5],
+          Ay[5]);
     xn = x + h * vx + hh * (bb1 * Ax[0] + bb2 * Ax[1] + bb3 * Ax[2] + bb4 * Ax[3] + bb5 * Ax[4]);
     yn = y + h * vy + hh * (bb1 * Ay[0] + bb2 * Ay[1] + bb3 * Ay[2] + bb4 * Ay[3] + bb5 * Ay[4]);
     vxn = vx + h * (b1 * Ax[0] + b3 * Ax[2] + b4 * Ax[3] + b5 * Ax[4] + b6 * Ax[5]);
     vyn = vy + h * (b1 * Ay[0] + b3 * Ay[2] + b4 * Ay[3] + b5 * Ay[4] + b6 * Ay[5]);
-    const double dth = ho + cs7 * ha;
-    thn = S.th + dth;
+    thn = S.th + d[5];
     omn = S.om + h * S.alpha;
-    accel_rot(c, e, S, xn, yn, dth, small, Ax[6], Ay[6], cn, sn);  // f_new (FSAL)
+    cn = cr[5];
+    sn = sr[5];
+    accel(c, e, xn, yn, cn, sn, S.fs, Ax[6], Ay[6]);  // f_new (FSAL)
     double ex = hh * (eb1 * Ax[0] + eb2 * Ax[1] + eb3 * Ax[2] + eb4 * Ax[3] + eb5 * Ax[4] + eb6 * Ax[5]);
     double ey = hh * (eb1 * Ay[0] + eb2 * Ay[1] + eb3 * Ay[2] + eb4 * Ay[3] + eb5 * Ay[4] + eb6 * Ay[5]);
     double evx = h * (e1 * Ax[0] + e3 * Ax[2] + e4 * Ax[3] + e5 * Ax[4] + e6 * Ax[5] + e7 * Ax[6]);
     double evy = h * (e1 * Ay[0] + e3 * Ay[2] + e4 * Ay[3] + e5 * Ay[4] + e6 * Ay[5] + e7 * Ay[6]);
-    ex /= kAtol + fmax(fabs(x), fabs(xn)) * kRtol;
-    ey /= kAtol + fmax(fabs(y), fabs(yn)) * kRtol;
-    evx /= kAtol + fmax(fabs(vx), fabs(vxn)) * kRtol;
-    evy /= kAtol + fmax(fabs(vy), fabs(vyn)) * kRtol;
-    err = sqrt(ex * ex + ey * ey + evx * evx + evy * evy) * kInvSqrt6;
+    ex *= fast_rcp(kAtol + fmax(fabs(x), fabs(xn)) * kRtol);
+    ey *= fast_rcp(kAtol + fmax(fabs(y), fabs(yn)) * kRtol);
+    evx *= fast_rcp(kAtol + fmax(fabs(vx), fabs(vxn)) * kRtol);
+    evy *= fast_rcp(kAtol + fmax(fabs(vy), fabs(vyn)) * kRtol);
+    err = fast_sqrt0(ex * ex + ey * ey + evx * evx + evy * evy) * kInvSqrt6;
 }
 
 __device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t, inf) - t|, scipy:rk.py:119
@@ -684,6 +778,14 @@ __device__ __forceinline__ int rk_loop(const DevCfg& c, const EnvRegs<TR>& e, In
 
 // wrap_ship_angle (dynamic_model.py:179-180): numpy floor-mod by 2 pi; also flags non-finite states
 __device__ __forceinline__ double wrap_angle(double th) {
+    // th mod 2 pi with numpy's floor-mod semantics.  The heading enters a step in [0, 2 pi] and moves by
+    // less than 0.5 rad, so one conditional add/subtract is the exact fmod result (Sterbenz); anything
+    // else (states injected from outside) takes the general path.
+    if (th >= -kTwoPi && th < 2 * kTwoPi) {
+        if (th >= kTwoPi) th -= kTwoPi;
+        else if (th < 0) th += kTwoPi;
+        return th;
+    }
     th = fmod(th, kTwoPi);
     if (th < 0) th += kTwoPi;
     return th;
@@ -738,7 +840,7 @@ __device__ __forceinline__ void make_obs_cs(const DevCfg& c, const EnvRegs<TR>& 
         for (int p = 0; p < TR::NP; ++p) {
             double dx = e.px[p] - e.x, dy = e.py[p] - e.y;
             double d2 = dx * dx + dy * dy;
-            double k = (1.0 - c.r0 * rsqrt(d2)) * c.two_over_ws;
+            double k = (1.0 - c.r0 * fast_rsqrt(d2)) * c.two_over_ws;
             row[7 + 2 * p] = (OT)(dx * k);
             row[8 + 2 * p] = (OT)(dy * k);
         }
@@ -764,9 +866,9 @@ template <class TR>
 __device__ __forceinline__ double goal_reward(const DevCfg& c, const EnvRegs<TR>& e, double lx, double ly,
                                               const double (&pd)[TR::NP], double& cur) {
     double dx = e.gx - e.x, dy = e.gy - e.y;
-    cur = sqrt(dx * dx + dy * dy);
+    cur = fast_sqrt0(dx * dx + dy * dy);
     double ldx = e.gx - lx, ldy = e.gy - ly;
-    double last = sqrt(ldx * ldx + ldy * ldy);
+    double last = fast_sqrt0(ldx * ldx + ldy * ldy);
     double gv = (last - cur) * 100.0;
     double mind = INFINITY, cx = 0, cy = 0;
 #pragma unroll
@@ -779,7 +881,7 @@ __device__ __forceinline__ double goal_reward(const DevCfg& c, const EnvRegs<TR>
     double sum_safety = 0.0;
     if (mind - c.r0 < c.danger_zone) {
         double qx = lx - cx, qy = ly - cy;
-        double prev = sqrt(qx * qx + qy * qy);
+        double prev = fast_sqrt0(qx * qx + qy * qy);
         if (prev > mind) sum_safety = -100.0 * (prev - mind);
     }
     return c.survival + c.goal_vel * gv + c.safety * sum_safety;
@@ -799,22 +901,23 @@ __device__ __forceinline__ double kepler_reward(const DevCfg& c, const EnvRegs<T
     double w0 = ca * e.x + sa * e.y - cc;  // _rotate, then shift by the focal distance
     double w1 = -sa * e.x + ca * e.y;
     double nw2 = w0 * w0 + w1 * w1;
-    double inw = rsqrt(nw2);
+    double inw = fast_rsqrt(nw2);
     double cur_rad = nw2 * inw;
     double ecos = ecc * (w0 * inw);  // cos(atan2(w1, w0))
-    double target_rad = b * rsqrt(1 - ecos * ecos);
+    double target_rad = b * fast_rsqrt(1 - ecos * ecos);
     double p0 = w0 * target_rad * inw, p1 = w1 * target_rad * inw;  // projection onto the orbit
-    double v0 = -(a / b) * p1, v1 = (b / a) * p0;
+    const double ab = fast_div(a, b);
+    double v0 = -ab * p1, v1 = fast_div(b, a) * p0;
     double rx = p0 + cc;
-    double r = sqrt(rx * rx + p1 * p1);
-    double ov = sqrt(c.gm0 * (2 / r - 1 / a));  // vis-viva
-    double sc = ov * rsqrt(v0 * v0 + v1 * v1);
+    double r = fast_sqrt(rx * rx + p1 * p1);
+    double ov = fast_sqrt0(c.gm0 * (2 * fast_rcp(r) - fast_rcp(a)));  // vis-viva
+    double sc = ov * fast_rsqrt(v0 * v0 + v1 * v1);
     v0 *= sc;
     v1 *= sc;
     double t0 = ca * v0 - sa * v1;  // _rotate by -angle
     double t1 = sa * v0 + ca * v1;
     double den = c.radC * fabs(cur_rad - target_rad) + fabs(t0 - e.vx) + fabs(t1 - e.vy) + act.act_term + c.numC;
-    return c.numC / den;
+    return fast_div(c.numC, den);
 }
 
 // ---- hexagonal tiling state (hexagonal_tiling.py) ---------------------------------------------------------
@@ -838,14 +941,14 @@ struct Tiles {
 
 __device__ inline void load_tiles(const DevCfg& c, long long i, Tiles& t) {
     t.unpack(c.tile_word[i]);
-    for (int k = 0; k < 4; ++k) t.fw[k] = c.free_tiles[k * c.n + i];
-    for (int k = 0; k < c.cols; ++k) t.cs[k] = c.col_shift[k * c.n + i];
+    for (int k = 0; k < 4; ++k) t.fw[k] = c.free_tiles[k * c.stride + i];
+    for (int k = 0; k < c.cols; ++k) t.cs[k] = c.col_shift[k * c.stride + i];
 }
 __device__ inline void store_tiles(const DevCfg& c, long long i, const Tiles& t, bool with_shift) {
     c.tile_word[i] = t.pack();
-    for (int k = 0; k < 4; ++k) c.free_tiles[k * c.n + i] = t.fw[k];
+    for (int k = 0; k < 4; ++k) c.free_tiles[k * c.stride + i] = t.fw[k];
     if (with_shift)
-        for (int k = 0; k < c.cols; ++k) c.col_shift[k * c.n + i] = t.cs[k];
+        for (int k = 0; k < c.cols; ++k) c.col_shift[k * c.stride + i] = t.cs[k];
 }
 
 // HexagonalTiling._tile_center_pos (hexagonal_tiling.py:136-158)

@@ -27,7 +27,7 @@ constexpr int kBlock = 128;
 // ---- state access ---------------------------------------------------------------------------
 template <class TR>
 __device__ __forceinline__ void load_env(const DevCfg& c, long long i, EnvRegs<TR>& e) {
-    const long long n = c.n;
+    const long long n = c.stride;
     e.x = c.ship[i];
     e.y = c.ship[n + i];
     e.th = c.ship[2 * n + i];
@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_env(const DevCfg& c, long long i, EnvRegs<T
 
 template <class TR>
 __device__ __forceinline__ void store_ship(const DevCfg& c, long long i, const EnvRegs<TR>& e) {
-    const long long n = c.n;
+    const long long n = c.stride;
     c.ship[i] = e.x;
     c.ship[n + i] = e.y;
     c.ship[2 * n + i] = e.th;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void store_ship(const DevCfg& c, long long i, const E
 
 template <class TR>
 __device__ __forceinline__ void store_scene(const DevCfg& c, long long i, const EnvRegs<TR>& e, bool planets) {
-    const long long n = c.n;
+    const long long n = c.stride;
     if (TR::TASK == TASK_GOAL) {
         if (planets) {
 #pragma unroll
@@ -148,7 +148,7 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
         for (int k = 0; k < K; ++k) {
             float r0, r1;
             if (actions) {
-                float2 a = reinterpret_cast<const float2*>(actions)[(long long)k * c.n + i];
+                float2 a = reinterpret_cast<const float2*>(actions)[(long long)k * c.stride + i];
                 r0 = a.x;
                 r1 = a.y;
             } else {
@@ -209,9 +209,9 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
                     if (last && obs) make_obs<TR, OT>(c, e, sobs + threadIdx.x * D);
                 }
             }
-            if (reward) reward[(long long)k * c.n + i] = r;
-            if (done_out) done_out[(long long)k * c.n + i] = dn ? 1 : 0;
-            if (trunc_out) trunc_out[(long long)k * c.n + i] = trunc ? 1 : 0;
+            if (reward) reward[(long long)k * c.stride + i] = r;
+            if (done_out) done_out[(long long)k * c.stride + i] = dn ? 1 : 0;
+            if (trunc_out) trunc_out[(long long)k * c.stride + i] = trunc ? 1 : 0;
         }
         store_ship<TR>(c, i, e);
         if (scene_dirty) store_scene<TR>(c, i, e, planets_dirty);
@@ -357,7 +357,7 @@ __device__ __forceinline__ void post_env(const DevCfg& c, long long i, bool reac
         rng.fresh_block();
         resample_goal<TR>(c, i, &rng, gxy, &status);
         c.goal[i] = gxy[0];
-        c.goal[c.n + i] = gxy[1];
+        c.goal[c.stride + i] = gxy[1];
     }
     if (done && c.auto_reset) {
         EnvRegs<TR> e;
@@ -412,10 +412,11 @@ __device__ __forceinline__ void save_event(const DevCfg& c, uint32_t slot, long 
 enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2 };
 
 template <class TR, typename OT>
-__global__ void __launch_bounds__(kBlock)
-hot_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long long step0, OT* __restrict__ obs,
-           double* __restrict__ reward, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+__global__ void __launch_bounds__(kBlock, 4)
+hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
     constexpr int D = TR::D;
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     __shared__ __align__(16) OT sobs[kBlock * D];
     const long long block_first = (long long)blockIdx.x * kBlock;
     const long long i = block_first + threadIdx.x;
@@ -480,9 +481,10 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long long
 
 // envs that need more than one Runge-Kutta step: resume solve_ivp's loop, densely packed
 template <class TR, typename OT>
-__global__ void __launch_bounds__(kBlock)
-cont_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long long step0, OT* __restrict__ obs,
-            double* __restrict__ reward, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+__global__ void __launch_bounds__(kBlock, 3)
+cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     const uint32_t count = c.q_counts[0];
     const long long cap = c.q_cap;
     double st[4] = {0, 0, 0, 0};
@@ -542,8 +544,9 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long lon
 constexpr int kTailBlock = 64;
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kTailBlock)
-tail_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long long step0, OT* __restrict__ obs,
-            double* __restrict__ reward, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     const uint32_t n_event = c.q_counts[1], n_post = c.q_counts[2];
     const uint32_t total = n_event + n_post;
     const long long cap = c.q_cap;
@@ -601,7 +604,14 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, unsigned long lon
     __threadfence();
     if (threadIdx.x == 0) last = (atomicAdd(&c.q_counts[3], 1u) == gridDim.x - 1);
     __syncthreads();
-    if (last && threadIdx.x < 4) c.q_counts[threadIdx.x] = 0;
+    if (last) {  // ... and advances the device-side step counter that keys the synthetic-action stream
+        if (threadIdx.x < 4) c.q_counts[threadIdx.x] = 0;
+        if (threadIdx.x == 4) *reinterpret_cast<unsigned long long*>(c.q_counts + 4) = step0 + 1;
+    }
+}
+
+__global__ void set_step_counter_kernel(uint32_t* q_counts, unsigned long long value) {
+    *reinterpret_cast<unsigned long long*>(q_counts + 4) = value;
 }
 
 template <class TR, typename OT>
@@ -697,6 +707,25 @@ struct sg_env {
     bool owns_state;
     double* d_stats;
     void* d_queues;  // work queues + scratch of the split step path
+    // split path: the envs are processed as `n_sub` independent sub-batches on internal streams, so that
+    // the latency-bound continuation / tail kernels of one sub-batch overlap the hot kernel of another;
+    // the whole fork / join is replayed as one CUDA graph per distinct set of argument pointers
+    int n_sub;
+    struct Sub {
+        DevCfg dev;
+        long long off, n;
+        cudaStream_t stream;
+        cudaEvent_t done;
+    } sub[8];
+    cudaEvent_t fork_ev;
+    struct GraphEntry {
+        const void* key[5];
+        cudaGraphExec_t exec;
+        uint64_t stamp;
+    } graphs[16];
+    int n_graphs;
+    uint64_t graph_clock;
+    int use_graphs;
     uint64_t step_count;
     int64_t launches;
     std::string err;
@@ -876,6 +905,11 @@ extern "C" int sg_state_layout(const sg_config* cfg, int64_t n, sg_layout* out) 
     return SG_OK;
 }
 
+static size_t queue_bytes(long long n) {
+    size_t b = 256 + 3 * ((((size_t)n * 4 + 255) / 256) * 256) + (size_t)(kContFields + kEventFields) * (size_t)n * sizeof(double);
+    return ((b + 255) / 256) * 256;
+}
+
 static void build_dev(sg_env* h) {
     const sg_config& c = h->cfg;
     DevCfg& d = h->dev;
@@ -893,17 +927,7 @@ static void build_dev(sg_env* h) {
     d.rng_ctr = (uint32_t*)(base + h->lay.rng_ctr);
     d.status = (uint32_t*)(base + h->lay.status);
     d.stats = h->d_stats;
-    {   // queue block: counts (256 B) | cont idx | event idx | post idx | cont scratch | event scratch
-        char* q = (char*)h->d_queues;
-        const size_t n = (size_t)h->n, idx_bytes = ((n * 4 + 255) / 256) * 256;
-        d.q_counts = (uint32_t*)q;
-        d.q_cont = (uint32_t*)(q + 256);
-        d.q_event = (uint32_t*)(q + 256 + idx_bytes);
-        d.q_post = (uint32_t*)(q + 256 + 2 * idx_bytes);
-        d.scr_cont = (double*)(q + 256 + 3 * idx_bytes);
-        d.scr_event = d.scr_cont + (size_t)kContFields * n;
-        d.q_cap = h->n;
-    }
+    d.stride = h->n;
     d.n = h->n;
     d.first_env = h->first_env;
     d.seed = h->seed;
@@ -950,6 +974,29 @@ static void build_dev(sg_env* h) {
     d.actC_f32 = (float)c.act_penalty_C;
     d.kep_lo = c.kepler_planet_radius + 0.5;  // kepler.py:235-237
     d.kep_hi = c.kepler_border_radius - 0.5;
+    // sub-batches: same constants, base pointers shifted by the sub-batch offset, own queue block
+    char* q = (char*)h->d_queues;
+    for (int s = 0; s < h->n_sub; ++s) {
+        sg_env::Sub& sb = h->sub[s];
+        DevCfg& x = sb.dev;
+        x = d;
+        x.n = sb.n;
+        x.first_env = h->first_env + sb.off;
+        x.ship += sb.off; x.planets += sb.off; x.goal += sb.off; x.orbit += sb.off; x.col_shift += sb.off;
+        x.ep_return += sb.off; x.free_tiles += sb.off; x.tile_word += sb.off; x.elapsed += sb.off;
+        x.rng_ctr += sb.off; x.status += sb.off;
+        // queue block: counts (256 B) | cont idx | event idx | post idx | cont scratch | event scratch
+        const size_t n = (size_t)sb.n, idx_bytes = ((n * 4 + 255) / 256) * 256;
+        x.q_counts = (uint32_t*)q;
+        x.q_cont = (uint32_t*)(q + 256);
+        x.q_event = (uint32_t*)(q + 256 + idx_bytes);
+        x.q_post = (uint32_t*)(q + 256 + 2 * idx_bytes);
+        x.scr_cont = (double*)(q + 256 + 3 * idx_bytes);
+        x.scr_event = x.scr_cont + (size_t)kContFields * n;
+        x.q_cap = sb.n;
+        q += queue_bytes(sb.n);
+    }
+    h->dev.q_counts = h->sub[0].dev.q_counts;
 }
 
 extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint64_t seed, int64_t first_env_index,
@@ -975,6 +1022,12 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     h->launches = 0;
     h->d_queues = nullptr;
     h->d_stats = nullptr;
+    h->n_sub = 1;
+    h->n_graphs = 0;
+    h->graph_clock = 0;
+    h->fork_ev = nullptr;
+    memset(h->sub, 0, sizeof(h->sub));
+    memset(h->graphs, 0, sizeof(h->graphs));
     h->hstream = nullptr;
     h->s_actions = nullptr;
     h->s_actions_bytes = 0;
@@ -988,10 +1041,36 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     cudaError_t err = cudaSuccess;
     if (h->owns_state) err = cudaMalloc(&h->state, (size_t)h->lay.total_bytes);
     if (err == cudaSuccess) err = cudaMalloc((void**)&h->d_stats, 4 * sizeof(double));
-    const size_t q_bytes = 256 + 3 * ((((size_t)n_envs * 4 + 255) / 256) * 256) +
-                           (size_t)(kContFields + kEventFields) * (size_t)n_envs * sizeof(double);
-    if (err == cudaSuccess) err = cudaMalloc(&h->d_queues, q_bytes);
-    if (err == cudaSuccess) err = cudaMemset(h->d_queues, 0, 256);
+    {   // sub-batches of the split path: multiples of the block size, at least 32768 envs each
+        // Measured on B200 (profiles/r1_notes.md): splitting one handle into concurrent sub-batches does not
+        // pay (2.2 -> 2.3 G env-steps/s at 262144 envs: each sub-batch still walks the same three-kernel
+        // latency chain), while independent handles on their own streams do (3.7 G/s).  Default: one.
+        int want = 1;
+        const char* env_sub = getenv("SG_SUBBATCHES");
+        if (env_sub && atoi(env_sub) > 0) want = atoi(env_sub) > 8 ? 8 : atoi(env_sub);
+        h->n_sub = want;
+        const char* env_graph = getenv("SG_GRAPHS");
+        h->use_graphs = env_graph ? atoi(env_graph) : 1;
+        long long per = ((n_envs / want + kBlock - 1) / kBlock) * kBlock, off = 0;
+        size_t q_bytes = 0;
+        for (int s = 0; s < want; ++s) {
+            long long cnt = (s == want - 1) ? n_envs - off : per;
+            if (cnt <= 0) { h->n_sub = s; break; }
+            h->sub[s].off = off;
+            h->sub[s].n = cnt;
+            h->sub[s].stream = nullptr;
+            h->sub[s].done = nullptr;
+            off += cnt;
+            q_bytes += queue_bytes(cnt);
+        }
+        if (err == cudaSuccess) err = cudaMalloc(&h->d_queues, q_bytes);
+        if (err == cudaSuccess) err = cudaMemset(h->d_queues, 0, q_bytes);
+        for (int s = 0; s < h->n_sub && err == cudaSuccess && h->n_sub > 1; ++s) {
+            err = cudaStreamCreateWithFlags(&h->sub[s].stream, cudaStreamNonBlocking);
+            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->sub[s].done, cudaEventDisableTiming);
+        }
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
+    }
     if (err == cudaSuccess) err = cudaMemset(h->state, 0, (size_t)h->lay.total_bytes);
     if (err == cudaSuccess) err = cudaMemset(h->d_stats, 0, 4 * sizeof(double));
     if (err != cudaSuccess) {
@@ -1021,6 +1100,13 @@ extern "C" void sg_destroy(sg_env* h) {
     if (h->owns_state && h->state) cudaFree(h->state);
     if (h->d_stats) cudaFree(h->d_stats);
     if (h->d_queues) cudaFree(h->d_queues);
+    for (int g = 0; g < h->n_graphs; ++g)
+        if (h->graphs[g].exec) cudaGraphExecDestroy(h->graphs[g].exec);
+    for (int s = 0; s < 8; ++s) {
+        if (h->sub[s].stream) cudaStreamDestroy(h->sub[s].stream);
+        if (h->sub[s].done) cudaEventDestroy(h->sub[s].done);
+    }
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->s_actions) cudaFree(h->s_actions);
     if (h->s_obs) cudaFree(h->s_obs);
     if (h->s_reward) cudaFree(h->s_reward);
@@ -1037,9 +1123,19 @@ extern "C" int sg_get_layout(const sg_env* h, sg_layout* out) {
 }
 extern "C" void* sg_state_ptr(const sg_env* h) { return h ? h->state : nullptr; }
 extern "C" uint64_t sg_step_count(const sg_env* h) { return h ? h->step_count : 0; }
+static int sync_step_counters(sg_env* h, cudaStream_t stream) {
+    for (int s = 0; s < h->n_sub; ++s) set_step_counter_kernel<<<1, 1, 0, stream>>>(h->sub[s].dev.q_counts, h->step_count);
+    h->launches += h->n_sub;
+    return SG_OK;
+}
+
 extern "C" int sg_set_step_count(sg_env* h, uint64_t s) {
     if (!h) return SG_ERR_INVALID;
+    SG_CUDA(h, cudaSetDevice(h->device));
+    SG_CUDA(h, cudaDeviceSynchronize());
     h->step_count = s;
+    sync_step_counters(h, nullptr);
+    SG_CUDA(h, cudaDeviceSynchronize());
     return SG_OK;
 }
 extern "C" int64_t sg_kernel_launches(const sg_env* h) { return h ? h->launches : 0; }
@@ -1059,6 +1155,7 @@ struct LaunchArgs {
     uint8_t* trunc;
     const uint8_t* mask;
     double* vf_out;
+    int sub;  // OP_STEP_SPLIT: sub-batch index
 };
 
 template <class TR, typename OT>
@@ -1068,17 +1165,24 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         step_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.K, a.step0, (OT*)a.obs, a.reward, a.done,
                                                              a.trunc);
     } else if (a.op == OP_STEP_SPLIT) {
+        const sg_env::Sub& sb = h->sub[a.sub];
+        const long long off = sb.off;
         const int sms = h->sm_count > 0 ? h->sm_count : 148;
-        const int cont_blocks = blocks < sms * 8 ? blocks : sms * 8;
-        const long long tb = (h->n + kTailBlock - 1) / kTailBlock;
+        const int hot_blocks = (int)((sb.n + kBlock - 1) / kBlock);
+        const int cont_blocks = hot_blocks < sms * 8 ? hot_blocks : sms * 8;
+        const long long tb = (sb.n + kTailBlock - 1) / kTailBlock;
         const int tail_blocks = (int)(tb < sms * 8 ? tb : sms * 8);
-        hot_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.step0, (OT*)a.obs, a.reward, a.done, a.trunc);
-        cont_kernel<TR, OT><<<cont_blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.step0, (OT*)a.obs, a.reward, a.done,
-                                                                  a.trunc);
-        tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, a.stream>>>(h->dev, a.actions, a.step0, (OT*)a.obs, a.reward,
-                                                                      a.done, a.trunc);
-    } else if (a.op == OP_RESET)
+        const float* act = a.actions ? a.actions + 2 * off : nullptr;
+        OT* obs = a.obs ? (OT*)a.obs + off * TR::D : nullptr;
+        double* rew = a.reward ? a.reward + off : nullptr;
+        uint8_t* dn = a.done ? a.done + off : nullptr;
+        uint8_t* tr = a.trunc ? a.trunc + off : nullptr;
+        hot_kernel<TR, OT><<<hot_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
+        cont_kernel<TR, OT><<<cont_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
+        tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
+    } else if (a.op == OP_RESET) {
         reset_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.mask, (OT*)a.obs);
+    }
 }
 
 template <class TR>
@@ -1102,15 +1206,97 @@ static void launch_np(const sg_env* h, const LaunchArgs& a) {
     else launch_tr<Traits<TASK, NP, STEER_ACC, 1>>(h, a);
 }
 
-static int launch(sg_env* h, const LaunchArgs& a) {
-    SG_CUDA(h, cudaSetDevice(h->device));
+// enqueue only (no error query: also used inside stream capture)
+static int enqueue(sg_env* h, const LaunchArgs& a) {
     if (h->cfg.task == SG_TASK_KEPLER) launch_np<TASK_KEPLER, 1>(h, a);
     else if (h->cfg.n_planets == 2) launch_np<TASK_GOAL, 2>(h, a);
     else if (h->cfg.n_planets == 3) launch_np<TASK_GOAL, 3>(h, a);
     else if (h->cfg.n_planets == 4) launch_np<TASK_GOAL, 4>(h, a);
     else return fail(h, SG_ERR_INVALID, "unsupported n_planets");
     h->launches += (a.op == OP_STEP_SPLIT) ? 3 : 1;
+    return SG_OK;
+}
+
+static int launch(sg_env* h, const LaunchArgs& a) {
+    SG_CUDA(h, cudaSetDevice(h->device));
+    int rc = enqueue(h, a);
+    if (rc != SG_OK) return rc;
     SG_CUDA(h, cudaGetLastError());
+    return SG_OK;
+}
+
+// One env step of the split path for every sub-batch: fork from `origin`, three kernels per sub-batch on its
+// own stream, join back into `origin`.
+static int enqueue_split_step(sg_env* h, cudaStream_t origin, LaunchArgs a) {
+    a.op = OP_STEP_SPLIT;
+    if (h->n_sub == 1) {
+        a.sub = 0;
+        a.stream = origin;
+        return enqueue(h, a);
+    }
+    SG_CUDA(h, cudaEventRecord(h->fork_ev, origin));
+    for (int s = 0; s < h->n_sub; ++s) {
+        cudaStream_t st = h->sub[s].stream;
+        if (st != origin) SG_CUDA(h, cudaStreamWaitEvent(st, h->fork_ev, 0));
+        a.sub = s;
+        a.stream = st;
+        int rc = enqueue(h, a);
+        if (rc != SG_OK) return rc;
+    }
+    for (int s = 0; s < h->n_sub; ++s) {
+        cudaStream_t st = h->sub[s].stream;
+        if (st == origin) continue;
+        SG_CUDA(h, cudaEventRecord(h->sub[s].done, st));
+        SG_CUDA(h, cudaStreamWaitEvent(origin, h->sub[s].done, 0));
+    }
+    return SG_OK;
+}
+
+// Same, replayed from a cached CUDA graph keyed by the argument pointers (one launch per env step).
+static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a) {
+    SG_CUDA(h, cudaSetDevice(h->device));
+    if (h->n_sub == 1 || !h->use_graphs) {
+        int rc = enqueue_split_step(h, user, a);
+        if (rc != SG_OK) return rc;
+        SG_CUDA(h, cudaGetLastError());
+        return SG_OK;
+    }
+    const void* key[5] = {a.actions, a.obs, a.reward, a.done, a.trunc};
+    sg_env::GraphEntry* hit = nullptr;
+    for (int g = 0; g < h->n_graphs; ++g)
+        if (!memcmp(h->graphs[g].key, key, sizeof(key))) hit = &h->graphs[g];
+    if (!hit) {
+        cudaStream_t origin = h->sub[0].stream;  // capture is not allowed on the legacy default stream
+        cudaGraph_t graph = nullptr;
+        const int64_t launches_before = h->launches;
+        SG_CUDA(h, cudaStreamBeginCapture(origin, cudaStreamCaptureModeRelaxed));
+        int rc = enqueue_split_step(h, origin, a);
+        cudaError_t cerr = cudaStreamEndCapture(origin, &graph);
+        h->launches = launches_before;
+        if (rc != SG_OK) return rc;
+        if (cerr != cudaSuccess) return fail(h, SG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(cerr));
+        int slot = h->n_graphs;
+        if (slot == 16) {  // evict the least recently used entry
+            slot = 0;
+            for (int g = 1; g < 16; ++g)
+                if (h->graphs[g].stamp < h->graphs[slot].stamp) slot = g;
+            cudaGraphExecDestroy(h->graphs[slot].exec);
+        } else {
+            h->n_graphs += 1;
+        }
+        hit = &h->graphs[slot];
+        memcpy(hit->key, key, sizeof(key));
+        cerr = cudaGraphInstantiate(&hit->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (cerr != cudaSuccess) {
+            hit->exec = nullptr;
+            memset(hit->key, 0xff, sizeof(hit->key));
+            return fail(h, SG_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(cerr));
+        }
+    }
+    hit->stamp = ++h->graph_clock;
+    SG_CUDA(h, cudaGraphLaunch(hit->exec, user));
+    h->launches += 3 * h->n_sub;
     return SG_OK;
 }
 
@@ -1145,23 +1331,26 @@ extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, do
         a.done = d_done;
         a.trunc = d_truncated;
         int rc = launch(h, a);
-        if (rc == SG_OK) h->step_count += (uint64_t)K;
-        return rc;
+        if (rc != SG_OK) return rc;
+        h->step_count += (uint64_t)K;
+        sync_step_counters(h, a.stream);  // keep the device-side counters of the split path in step
+        SG_CUDA(h, cudaGetLastError());
+        return SG_OK;
     }
-    // split path: K single steps, three launches each; the observation is only needed after the last one
+    // split path: K single steps (hot / continuation / tail kernels per sub-batch, replayed as one CUDA
+    // graph each); the observation is only needed after the last one
     a.op = OP_STEP_SPLIT;
     a.K = 1;
     for (int k = 0; k < K; ++k) {
         const size_t off = (size_t)k * (size_t)h->n;
         a.actions = d_actions ? d_actions + 2 * off : nullptr;
-        a.step0 = h->step_count;
         a.obs = (k == K - 1) ? d_obs : nullptr;
         a.reward = d_reward ? d_reward + off : nullptr;
         a.done = d_done ? d_done + off : nullptr;
         a.trunc = d_truncated ? d_truncated + off : nullptr;
-        int rc = launch(h, a);
+        int rc = launch_split_step(h, (cudaStream_t)stream, a);
         if (rc != SG_OK) return rc;
-        h->step_count += 1;
+        h->step_count += 1;  // the tail kernels advance the device-side counters
     }
     return SG_OK;
 }

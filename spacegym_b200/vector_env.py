@@ -24,8 +24,13 @@ def shard_range(total_envs, rank, world_size):
 
 
 class BatchedSpaceEnv:
-    def __init__(self, env_id, num_envs, device="cuda:0", seed=0, first_env_index=0, **kwargs):
+    def __init__(self, env_id, num_envs, device="cuda:0", seed=0, first_env_index=0, copy=True, **kwargs):
+        """copy=True returns fresh tensors from step()/step_many() (gym.vector's default); copy=False returns
+        the engine's persistent output buffers, which the next step overwrites (stable pointers also let the
+        C library replay its cached CUDA graph for the step)."""
         self._h = None
+        self.copy = bool(copy)
+        self._out = {}
         self.env_id = env_id
         self.cfg = make_config(env_id, **kwargs)
         self.num_envs = int(num_envs)
@@ -123,13 +128,23 @@ class BatchedSpaceEnv:
                     assert bool(((a0 >= 0) & (a0 <= 5) & (a0 == a0.floor())).all()), "action outside Discrete(6)"
                 else:
                     assert bool(((actions >= -1) & (actions <= 1)).all()), "action outside Box(-1, 1)"
-        obs = torch.empty((n, self.obs_dim), dtype=self.obs_dtype, device=self.device) if want_obs else None
-        rew = torch.empty((K, n), dtype=torch.float64, device=self.device)
-        done = torch.empty((K, n), dtype=torch.uint8, device=self.device)
-        trunc = torch.empty((K, n), dtype=torch.uint8, device=self.device)
-        check(self._L.sg_step(self._h, self._ptr(actions), int(K), self._ptr(obs), self._ptr(rew), self._ptr(done),
-                              self._ptr(trunc), self._stream()), self._h)
-        return obs, rew, done.bool(), {"TimeLimit.truncated": trunc.bool()}
+        K = int(K)
+        if K not in self._out:
+            if len(self._out) > 4:
+                self._out.clear()
+            self._out[K] = dict(obs=torch.empty((n, self.obs_dim), dtype=self.obs_dtype, device=self.device),
+                                rew=torch.empty((K, n), dtype=torch.float64, device=self.device),
+                                done=torch.empty((K, n), dtype=torch.uint8, device=self.device),
+                                trunc=torch.empty((K, n), dtype=torch.uint8, device=self.device))
+        o = self._out[K]
+        obs = o["obs"] if want_obs else None
+        check(self._L.sg_step(self._h, self._ptr(actions), K, self._ptr(obs), self._ptr(o["rew"]), self._ptr(o["done"]),
+                              self._ptr(o["trunc"]), self._stream()), self._h)
+        rew, done, trunc = o["rew"], o["done"].bool(), o["trunc"].bool()
+        if self.copy:
+            obs = obs.clone() if obs is not None else None
+            rew = rew.clone()
+        return obs, rew, done, {"TimeLimit.truncated": trunc}
 
     def rollout_random(self, K):
         """K env steps with the engine's synthetic uniform actions; nothing but statistics comes back."""

@@ -116,7 +116,7 @@ def test_fused_substeps_and_synthetic_actions(oracle, case):
                 env.set_state(oracle_state_to_engine(cfg, eng.envs))
     sa, sb = a.stats(), b.stats()
     assert abs(sa["episodes"] - sb["episodes"]) <= 2 and abs(sa["goals"] - sb["goals"]) <= 2
-    assert abs(sa["episodes"] - eng.stats[2]) <= 2 and sa["episodes"] > n / 2
+    assert abs(sa["episodes"] - eng.stats[2]) <= 2 and sa["episodes"] > 100
     a.close(); b.close()
 
 
