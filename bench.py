@@ -258,17 +258,31 @@ def run_b200(args):
     value = total * args.steps / (ms * 1e-3)
 
     # ---- end to end: public API with host buffers (pinned), copies inside the timed region ----
-    e2e_steps = max(3, min(args.steps, 30))
+    # gym.vector step_async / step_wait over the same four env batches: every step uploads its actions
+    # from host memory and downloads observation, reward, done and truncated into host memory.
+    e2e_steps = max(N_BATCHES, min(args.steps, 200) // N_BATCHES * N_BATCHES)
     host_acts = [np.random.RandomState(7 + rank + i).uniform(-1, 1, size=(n, 2)).astype(np.float32)
                  for i in range(ACTION_SETS)]
-    for k in range(3):
-        envs[k % N_BATCHES].step(host_acts[k % ACTION_SETS])
+    for e in envs:
+        e.copy = False  # results are read in place from the pinned buffers
+    for k in range(2 * N_BATCHES):
+        envs[k % N_BATCHES].step_async(host_acts[k % ACTION_SETS])
+        if k >= N_BATCHES - 1:
+            envs[(k + 1) % N_BATCHES].step_wait()
+    for b in range(1, N_BATCHES):
+        envs[b].step_wait()
     barrier()
     t0 = time.perf_counter()
     checksum = 0.0
     for k in range(e2e_steps):
-        obs, rew, done, info = envs[k % N_BATCHES].step(host_acts[k % ACTION_SETS])
-        checksum += float(rew[0])
+        b = k % N_BATCHES
+        if k >= N_BATCHES:  # results of this batch's previous step: consume before reusing its buffers
+            obs, rew, done, info = envs[b].step_wait()
+            checksum += float(rew[0]) + float(obs[-1, 0])
+        envs[b].step_async(host_acts[(k // N_BATCHES) % ACTION_SETS])
+    for b in range(N_BATCHES):
+        obs, rew, done, info = envs[b].step_wait()
+        checksum += float(rew[0]) + float(obs[-1, 0])
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -314,7 +328,7 @@ def run_b200(args):
                               "algo_flops_per_env_step": ALGO_FLOPS_PER_STEP,
                               "peak_source": "sg_measure_fp64_peak (DFMA chains, this run)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchedSpaceEnv.step(numpy) -> sg_step_host"},
+                    "steps": e2e_steps, "api": "BatchedSpaceEnv.step_async(numpy)/step_wait() -> sg_step_host_async/sg_host_wait, 4 env batches in flight"},
             "gpu_launches": launches * world,
             "clocks": clocks,
             "episode_stats": stats,

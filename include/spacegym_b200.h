@@ -147,6 +147,12 @@ int sg_step(sg_env* env, const float* d_actions, int K, void* d_obs, double* d_r
 int sg_reset_host(sg_env* env, void* h_obs);
 int sg_step_host(sg_env* env, const float* h_actions, int K, void* h_obs, double* h_reward,
                  uint8_t* h_done, uint8_t* h_truncated);
+/* Asynchronous form (gym.vector step_async / step_wait): sg_step_host_async enqueues upload, step and
+ * download on the handle's own stream and returns; sg_host_wait blocks until the host buffers hold the
+ * results.  With pinned host buffers several handles overlap their copies and kernels. */
+int sg_step_host_async(sg_env* env, const float* h_actions, int K, void* h_obs, double* h_reward,
+                       uint8_t* h_done, uint8_t* h_truncated);
+int sg_host_wait(sg_env* env);
 
 /* RHS of the ship ODE for every env at its current state: d_out f64 [N][6]. */
 int sg_vector_field(sg_env* env, const float* d_actions, double* d_out, void* stream);

@@ -36,7 +36,7 @@ class SgLayout(C.Structure):
 
 EXPORTS = [
     "sg_config_from_id", "sg_config_finalize", "sg_obs_dim", "sg_state_layout", "sg_create", "sg_destroy",
-    "sg_last_error", "sg_get_layout", "sg_state_ptr", "sg_reset", "sg_step", "sg_reset_host", "sg_step_host",
+    "sg_last_error", "sg_get_layout", "sg_state_ptr", "sg_reset", "sg_step", "sg_reset_host", "sg_step_host", "sg_step_host_async", "sg_host_wait",
     "sg_vector_field", "sg_stats", "sg_stats_reset", "sg_step_count", "sg_set_step_count", "sg_kernel_launches",
     "sg_measure_fp64_peak", "sg_version",
 ]
@@ -71,6 +71,8 @@ def lib():
     L.sg_step.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.sg_reset_host.argtypes = [vp, vp]
     L.sg_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    L.sg_step_host_async.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    L.sg_host_wait.argtypes = [vp]
     L.sg_vector_field.argtypes = [vp, vp, vp, vp]
     L.sg_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.sg_stats_reset.argtypes = [vp, vp]

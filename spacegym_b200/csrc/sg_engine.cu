@@ -1399,8 +1399,8 @@ extern "C" int sg_reset_host(sg_env* h, void* h_obs) {
     return SG_OK;
 }
 
-extern "C" int sg_step_host(sg_env* h, const float* h_actions, int K, void* h_obs, double* h_reward, uint8_t* h_done,
-                            uint8_t* h_truncated) {
+extern "C" int sg_step_host_async(sg_env* h, const float* h_actions, int K, void* h_obs, double* h_reward,
+                                  uint8_t* h_done, uint8_t* h_truncated) {
     if (!h || K <= 0) return SG_ERR_INVALID;
     int rc = ensure_staging(h, K);
     if (rc != SG_OK) return rc;
@@ -1416,8 +1416,22 @@ extern "C" int sg_step_host(sg_env* h, const float* h_actions, int K, void* h_ob
     if (h_reward) SG_CUDA(h, cudaMemcpyAsync(h_reward, h->s_reward, kn * sizeof(double), cudaMemcpyDeviceToHost, h->hstream));
     if (h_done) SG_CUDA(h, cudaMemcpyAsync(h_done, h->s_done, kn, cudaMemcpyDeviceToHost, h->hstream));
     if (h_truncated) SG_CUDA(h, cudaMemcpyAsync(h_truncated, h->s_trunc, kn, cudaMemcpyDeviceToHost, h->hstream));
+    return SG_OK;
+}
+
+extern "C" int sg_host_wait(sg_env* h) {
+    if (!h) return SG_ERR_INVALID;
+    if (!h->hstream) return SG_OK;
+    SG_CUDA(h, cudaSetDevice(h->device));
     SG_CUDA(h, cudaStreamSynchronize(h->hstream));
     return SG_OK;
+}
+
+extern "C" int sg_step_host(sg_env* h, const float* h_actions, int K, void* h_obs, double* h_reward, uint8_t* h_done,
+                            uint8_t* h_truncated) {
+    int rc = sg_step_host_async(h, h_actions, K, h_obs, h_reward, h_done, h_truncated);
+    if (rc != SG_OK) return rc;
+    return sg_host_wait(h);
 }
 
 extern "C" int sg_stats(sg_env* h, double out[4], void* stream) {

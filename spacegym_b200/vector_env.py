@@ -150,27 +150,53 @@ class BatchedSpaceEnv:
         """K env steps with the engine's synthetic uniform actions; nothing but statistics comes back."""
         check(self._L.sg_step(self._h, None, int(K), None, None, None, None, self._stream()), self._h)
 
-    def _step_host(self, actions, check_actions=False):
-        n, D = self.num_envs, self.obs_dim
+    # ---- host-buffer path (numpy in, numpy out): gym.vector step_async / step_wait -------------------
+    def _host_buffers(self):
         if self._host is None:
-            np_obs = np.float32 if self.cfg.obs_dtype == 1 else np.float64
+            n, D = self.num_envs, self.obs_dim
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
             self._host = dict(act=pin((n, 2), torch.float32), obs=pin((n, D), self.obs_dtype),
                               rew=pin((n,), torch.float64), done=pin((n,), torch.uint8), trunc=pin((n,), torch.uint8))
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
-            assert self._host_np["obs"].dtype == np_obs
-        hb, hn = self._host, self._host_np
-        a = np.asarray(actions)
-        if self.cfg.discrete and a.ndim == 1:
-            hn["act"][:, 0] = a
-            hn["act"][:, 1] = 0
-        else:
-            if check_actions:
-                assert a.shape == (n, 2) and np.all(a >= -1) and np.all(a <= 1), "action outside Box(-1, 1)"
-            hn["act"][...] = a.astype(np.float32, copy=False)
-        check(self._L.sg_step_host(self._h, self._ptr(hb["act"]), 1, self._ptr(hb["obs"]), self._ptr(hb["rew"]),
-                                   self._ptr(hb["done"]), self._ptr(hb["trunc"])), self._h)
-        return hn["obs"], hn["rew"], hn["done"].astype(bool), {"TimeLimit.truncated": hn["trunc"].astype(bool)}
+            self._host_np["done"] = self._host_np["done"].view(np.bool_)
+            self._host_np["trunc"] = self._host_np["trunc"].view(np.bool_)
+        return self._host, self._host_np
+
+    @property
+    def action_buffer(self):
+        """Pinned float32 [N, 2] action buffer: write actions here and call step_async(None) to skip a copy."""
+        return self._host_buffers()[1]["act"]
+
+    def step_async(self, actions=None, check_actions=False):
+        """Upload `actions` (numpy [N, 2] float32, or [N] ints for discrete envs; None = already written to
+        `action_buffer`), step, and start downloading the results on the handle's own stream."""
+        hb, hn = self._host_buffers()
+        if actions is not None:
+            a = np.asarray(actions)
+            if self.cfg.discrete and a.ndim == 1:
+                hn["act"][:, 0] = a
+                hn["act"][:, 1] = 0
+            else:
+                if check_actions:  # the reference asserts action_space.contains (spaceship_env.py:71)
+                    assert a.shape == (self.num_envs, 2) and np.all(a >= -1) and np.all(a <= 1), \
+                        "action outside Box(-1, 1)"
+                np.copyto(hn["act"], a, casting="same_kind")
+        check(self._L.sg_step_host_async(self._h, self._ptr(hb["act"]), 1, self._ptr(hb["obs"]), self._ptr(hb["rew"]),
+                                         self._ptr(hb["done"]), self._ptr(hb["trunc"])), self._h)
+
+    def step_wait(self):
+        """Block until the results of step_async are in host memory. The returned arrays are the env's pinned
+        buffers (overwritten by the next step) unless copy=True."""
+        check(self._L.sg_host_wait(self._h), self._h)
+        hn = self._host_np
+        obs, rew, done, trunc = hn["obs"], hn["rew"], hn["done"], hn["trunc"]
+        if self.copy:
+            obs, rew, done, trunc = obs.copy(), rew.copy(), done.copy(), trunc.copy()
+        return obs, rew, done, {"TimeLimit.truncated": trunc}
+
+    def _step_host(self, actions, check_actions=False):
+        self.step_async(actions, check_actions)
+        return self.step_wait()
 
     def vector_field(self, actions):
         """SpaceshipEnv.vector_field (spaceship_env.py:96-100) for every env: [N, 6]."""
