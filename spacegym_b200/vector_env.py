@@ -23,6 +23,22 @@ def shard_range(total_envs, rank, world_size):
     return start, base + (1 if rank < rem else 0)
 
 
+def allreduce_stats(vals):
+    """Sum the 4-double episode statistics over torch.distributed ranks — the engine's only collective
+    (SURVEY.md §8e).  NCCL needs the tensor on the GPU; gloo (CPU tests) reduces it in place."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return vals
+    if dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = vals.to(dev)
+        dist.all_reduce(t)
+        return t.cpu()
+    t = vals.clone()
+    dist.all_reduce(t)
+    return t
+
+
 class BatchedSpaceEnv:
     def __init__(self, env_id, num_envs, device="cuda:0", seed=0, first_env_index=0, copy=True, **kwargs):
         """copy=True returns fresh tensors from step()/step_many() (gym.vector's default); copy=False returns
@@ -256,11 +272,9 @@ class BatchedSpaceEnv:
         buf = (C.c_double * 4)()
         check(self._L.sg_stats(self._h, buf, self._stream()), self._h)
         vals = torch.tensor(list(buf), dtype=torch.float64)
-        if allreduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            if torch.distributed.get_backend() == "nccl":
-                vals = vals.to(self.device)
-            torch.distributed.all_reduce(vals)
-            vals = vals.cpu()
+        if allreduce:
+            with torch.cuda.device(self.device):
+                vals = allreduce_stats(vals)
         return dict(zip(("return_sum", "length_sum", "episodes", "goals"), vals.tolist()))
 
     def stats_reset(self):
