@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENV_ID = "GoalContinuous3P-v0"
+ENV_KW = {}
 ENVS_PER_STEP = 262144
 N_BATCHES = 4
 ACTION_SETS = 4
@@ -184,7 +185,7 @@ def run_b200(args):
     n = args.envs
     total = n * world
     # envs sharded by contiguous global index range, no data-path collective
-    envs = [sg.make(ENV_ID, n, device=dev, seed=1000 + b, first_env_index=rank * n) for b in range(N_BATCHES)]
+    envs = [sg.make(ENV_ID, n, device=dev, seed=1000 + b, first_env_index=rank * n, **ENV_KW) for b in range(N_BATCHES)]
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     actions = [[(torch.rand((1, n, 2), device=dev, generator=gen) * 2 - 1).float().contiguous()
@@ -362,7 +363,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--env-id", default=None, help="benchmark another registered id (default: the BASELINE workload)")
+    ap.add_argument("--kwargs", default="{}", help="JSON dict of reference-style kwargs for --env-id")
     args = ap.parse_args()
+    global ENV_ID, ENV_KW
+    if args.env_id:
+        ENV_ID = args.env_id
+    ENV_KW = json.loads(args.kwargs)
     if args.impl == "reference":
         run_reference(args)
     else:

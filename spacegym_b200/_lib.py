@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libspacegym_b200.so")
+LIB_PATH = os.environ.get("SPACEGYM_B200_LIB", os.path.join(HERE, "libspacegym_b200.so"))
 
 
 class SgConfig(C.Structure):

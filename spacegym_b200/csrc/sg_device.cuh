@@ -123,8 +123,10 @@ struct DevCfg {
     uint32_t* status;
     double* stats;  // 4 doubles: sum return, sum length, episodes, goals
     // work queues of the split step path (library-owned scratch, empty between sg_step calls)
-    uint32_t* q_counts;   // [0] continuation, [1] event, [2] post, [3] block ticket, [4..5] u64 step counter
-    uint32_t* q_cont;     // env indices
+    uint32_t* q_counts;   // [0] continuation, [1] event, [2] post, [3] block ticket, [4..5] u64 step counter, [6] continuation 2
+    uint32_t* q_cont;     // env indices, first continuation queue (filled by the hot kernel)
+    uint32_t* q_cont2;    // second continuation queue (filled by the single-attempt continuation kernel)
+    double* scr_cont2;
     uint32_t* q_event;
     uint32_t* q_post;     // env index | reached << 30 | done << 31
     double* scr_cont;     // [13][cap]: x y th vx vy om cth sth Ax Ay h_abs t flags(lx, ly separately)
@@ -302,6 +304,10 @@ __device__ __forceinline__ void accel(const DevCfg& c, const EnvRegs<TR>& e, dou
     ay = fy * c.inv_mass;
 }
 
+template <class TR>
+__device__ __forceinline__ void event_values_from_pd(const DevCfg& c, double x, double y, double om,
+                                                     const double (&pd)[TR::NP], double (&g)[TR::NEV]);
+
 // ---- termination events (dynamic_model.py:183-217) -------------------------------------------------
 // order: planets..., world_max, world_min, angular velocity.  pd = planet-centre distances.
 template <class TR>
@@ -312,6 +318,28 @@ __device__ __forceinline__ void event_values(const DevCfg& c, const EnvRegs<TR>&
         double dx = e.px[p] - x, dy = e.py[p] - y;
         pd[p] = fast_sqrt(dx * dx + dy * dy);
     }
+    event_values_from_pd<TR>(c, x, y, om, pd, g);
+}
+
+// same, also returning 1 / distance (the lidar rows of the observation reuse it)
+template <class TR>
+__device__ __forceinline__ void event_values_inv(const DevCfg& c, const EnvRegs<TR>& e, double x, double y, double om,
+                                                 double (&g)[TR::NEV], double (&pd)[TR::NP], double (&ipd)[TR::NP]) {
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        double dx = e.px[p] - x, dy = e.py[p] - y;
+        const double d2 = dx * dx + dy * dy;
+        const double inv = fast_rsqrt(d2);
+        const double s = d2 * inv;
+        pd[p] = fma(fma(-s, s, d2), 0.5 * inv, s);
+        ipd[p] = inv;
+    }
+    event_values_from_pd<TR>(c, x, y, om, pd, g);
+}
+
+template <class TR>
+__device__ __forceinline__ void event_values_from_pd(const DevCfg& c, double x, double y, double om,
+                                                     const double (&pd)[TR::NP], double (&g)[TR::NEV]) {
     if (TR::TASK == TASK_GOAL) {
 #pragma unroll
         for (int p = 0; p < TR::NP; ++p) g[p] = pd[p] - c.r0;
@@ -637,7 +665,7 @@ template <class TR>
 __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e, const Integ<TR>& S, double h,
                                            double (&Ax)[7], double (&Ay)[7], double& xn, double& yn, double& thn,
                                            double& vxn, double& vyn, double& omn, double& cn, double& sn,
-                                           double& err) {
+                                           double& err2) {
     const double x = S.x, y = S.y, vx = S.vx, vy = S.vy;
     const double hh = h * h, ho = h * S.om, ha = hh * S.alpha;
     const bool small = fabs(ho) + fabs(ha) < 0.5;
@@ -684,7 +712,7 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     ey *= fast_rcp(kAtol + fmax(fabs(y), fabs(yn)) * kRtol);
     evx *= fast_rcp(kAtol + fmax(fabs(vx), fabs(vxn)) * kRtol);
     evy *= fast_rcp(kAtol + fmax(fabs(vy), fabs(vyn)) * kRtol);
-    err = fast_sqrt0(ex * ex + ey * ey + evx * evx + evy * evy) * kInvSqrt6;
+    err2 = (ex * ex + ey * ey + evx * evx + evy * evy) * (1.0 / 6.0);  // error_norm ** 2
 }
 
 __device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t, inf) - t|, scipy:rk.py:119
@@ -692,16 +720,18 @@ __device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t,
 }
 
 // step-size controller after an attempt (scipy:rk.py:145-165); returns true when the step is accepted
-__device__ __forceinline__ bool controller(double err, bool& rejected, bool more_steps, double& h_abs) {
-    if (err < 1) {
+// err2 = error_norm ** 2: `error_norm < 1` and `error_norm ** -0.2` are evaluated on the square
+// (x < 1 <=> x*x < 1 for x >= 0; err ** -0.2 = err2 ** -0.1), which saves the square root.
+__device__ __forceinline__ bool controller(double err2, bool& rejected, bool more_steps, double& h_abs) {
+    if (err2 < 1) {
         if (more_steps) {  // the next step size only matters if another step follows
-            double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+            double factor = (err2 == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err2, -0.1));
             if (rejected) factor = fmin(1.0, factor);
             h_abs *= factor;
         }
         return true;
     }
-    h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+    h_abs *= fmax(0.2, 0.9 * pow(err2, -0.1));
     rejected = true;
     return false;
 }
@@ -748,15 +778,15 @@ __device__ __forceinline__ int rk_loop(const DevCfg& c, const EnvRegs<TR>& e, In
     for (;;) {
         const double min_step = min_step_at(S.t);
         if (S.h_abs < min_step && !rejected) S.h_abs = min_step;
-        double Ax[7], Ay[7], xn, yn, thn, vxn, vyn, omn, cn, sn, err, h, t_new;
+        double Ax[7], Ay[7], xn, yn, thn, vxn, vyn, omn, cn, sn, err2, h, t_new;
         for (;;) {
             if (S.h_abs < min_step) return RK_FAILED;
             t_new = S.t + S.h_abs;
             if (t_new - T > 0) t_new = T;
             h = t_new - S.t;
             S.h_abs = fabs(h);
-            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err);
-            if (controller(err, rejected, t_new < T, S.h_abs)) break;
+            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
+            if (controller(err2, rejected, t_new < T, S.h_abs)) break;
         }
         rejected = false;
         double gn[TR::NEV];
@@ -826,6 +856,33 @@ __device__ __forceinline__ bool make_step(const DevCfg& c, EnvRegs<TR>& e, const
 
 // ---- observation (spaceship_env.py:113-140, kepler.py:172-187) ---------------------------------------
 // Lidar = unit(obj - pos) * (|obj - pos| - r) * 2 / ws, written without atan2/cos/sin.
+// observation when 1 / |planet - ship| is already known (from the event check at the same state)
+template <class TR, typename OT>
+__device__ __forceinline__ void make_obs_inv(const DevCfg& c, const EnvRegs<TR>& e, double cs, double sn,
+                                             const double (&ipd)[TR::NP], OT* row) {
+    row[0] = (OT)e.x;
+    row[1] = (OT)e.y;
+    row[2] = (OT)cs;
+    row[3] = (OT)sn;
+    row[4] = (OT)e.vx;
+    row[5] = (OT)e.vy;
+    row[6] = (OT)e.om;
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int p = 0; p < TR::NP; ++p) {
+            const double k = (1.0 - c.r0 * ipd[p]) * c.two_over_ws;
+            row[7 + 2 * p] = (OT)((e.px[p] - e.x) * k);
+            row[8 + 2 * p] = (OT)((e.py[p] - e.y) * k);
+        }
+        row[7 + 2 * TR::NP] = (OT)((e.gx - e.x) * c.two_over_ws);
+        row[8 + 2 * TR::NP] = (OT)((e.gy - e.y) * c.two_over_ws);
+    } else {
+        row[7] = (OT)e.ang;
+        row[8] = (OT)e.ecc;
+        row[9] = (OT)c.orbit_a;
+    }
+}
+
 template <class TR, typename OT>
 __device__ __forceinline__ void make_obs_cs(const DevCfg& c, const EnvRegs<TR>& e, double cs, double sn, OT* row) {
     row[0] = (OT)e.x;

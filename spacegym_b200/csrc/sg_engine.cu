@@ -255,7 +255,7 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
 // env (initial step selection + ONE attempt + epilogue) and appends the rest to compact queues, which
 // the continuation and tail kernels process with densely packed warps.
 // =================================================================================================
-constexpr int kContFields = 15;   // x y th vx vy om cth sth Ax Ay h_abs t lx ly rejected
+constexpr int kContFields = 28;   // x y th vx vy om cth sth Ax Ay h_abs t lx ly rejected | fs alpha act_term | scene[10]
 constexpr int kEventFields = 25;  // x y th vx vy om h t_old Ax[7] Ay[7] lx ly active
 constexpr uint32_t kPostReached = 1u << 30, kPostDone = 1u << 31, kPostIndex = (1u << 30) - 1;
 
@@ -306,11 +306,11 @@ __device__ __forceinline__ Act fetch_action(const DevCfg& c, const float* __rest
 // bookkeeping and outputs.  The goal resample / reset are NOT done here (post work).
 template <class TR, typename OT>
 __device__ __forceinline__ void finish_env(const DevCfg& c, long long i, EnvRegs<TR>& e, const Act& act, double lx,
-                                           double ly, const double (&pd)[TR::NP], bool dn, OT* obs_row, double cs,
-                                           double sn, double* __restrict__ reward, uint8_t* __restrict__ done_out,
-                                           uint8_t* __restrict__ trunc_out, double (&st)[4], bool& reached,
-                                           bool& done) {
-    if (obs_row) make_obs_cs<TR, OT>(c, e, cs, sn, obs_row);
+                                           double ly, const double (&pd)[TR::NP], const double (&ipd)[TR::NP], bool dn,
+                                           OT* obs_row, double cs, double sn, double* __restrict__ reward,
+                                           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
+                                           double (&st)[4], bool& reached, bool& done) {
+    if (obs_row) make_obs_inv<TR, OT>(c, e, cs, sn, ipd, obs_row);
     double r;
     reached = false;
     if (TR::TASK == TASK_GOAL) {
@@ -382,14 +382,60 @@ __device__ __forceinline__ void post_env(const DevCfg& c, long long i, bool reac
 }
 
 template <class TR>
-__device__ __forceinline__ void save_cont(const DevCfg& c, uint32_t slot, long long i, const Integ<TR>& S, double lx,
-                                          double ly, bool rejected) {
+__device__ __forceinline__ void save_cont(const DevCfg& c, uint32_t* q_idx, double* scr, uint32_t slot, long long i,
+                                          const Integ<TR>& S, double lx, double ly, bool rejected) {
     const long long cap = c.q_cap;
-    double* p = c.scr_cont + slot;
-    c.q_cont[slot] = (uint32_t)i;
+    double* p = scr + slot;
+    q_idx[slot] = (uint32_t)i;
     p[0 * cap] = S.x; p[1 * cap] = S.y; p[2 * cap] = S.th; p[3 * cap] = S.vx; p[4 * cap] = S.vy; p[5 * cap] = S.om;
     p[6 * cap] = S.cth; p[7 * cap] = S.sth; p[8 * cap] = S.Ax; p[9 * cap] = S.Ay; p[10 * cap] = S.h_abs;
     p[11 * cap] = S.t; p[12 * cap] = lx; p[13 * cap] = ly; p[14 * cap] = rejected ? 1.0 : 0.0;
+}
+
+// everything else the single-attempt continuation kernel needs, so that it reads coalesced scratch rows
+// instead of gathering the env's state by index
+template <class TR>
+__device__ __forceinline__ void save_cont_scene(const DevCfg& c, double* scr, uint32_t slot, const EnvRegs<TR>& e,
+                                                const Act& act) {
+    const long long cap = c.q_cap;
+    double* p = scr + slot;
+    p[15 * cap] = act.fs; p[16 * cap] = act.alpha; p[17 * cap] = act.act_term;
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int q = 0; q < TR::NP; ++q) {
+            p[(18 + 2 * q) * cap] = e.px[q];
+            p[(19 + 2 * q) * cap] = e.py[q];
+        }
+        p[(18 + 2 * TR::NP) * cap] = e.gx;
+        p[(19 + 2 * TR::NP) * cap] = e.gy;
+    } else {
+        p[18 * cap] = e.ecc;
+        p[19 * cap] = e.ang;
+    }
+}
+
+template <class TR>
+__device__ __forceinline__ void load_cont_scene(const DevCfg& c, const double* scr, uint32_t j, EnvRegs<TR>& e, Act& act) {
+    const long long cap = c.q_cap;
+    const double* p = scr + j;
+    act.fs = p[15 * cap]; act.alpha = p[16 * cap]; act.act_term = p[17 * cap];
+    act.w = 0.0;
+    e.x = e.y = e.th = e.vx = e.vy = e.om = 0.0;
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int q = 0; q < TR::NP; ++q) {
+            e.px[q] = p[(18 + 2 * q) * cap];
+            e.py[q] = p[(19 + 2 * q) * cap];
+        }
+        e.gx = p[(18 + 2 * TR::NP) * cap];
+        e.gy = p[(19 + 2 * TR::NP) * cap];
+        e.ecc = e.ang = 0.0;
+    } else {
+        e.px[0] = e.py[0] = 0.0;
+        e.gx = e.gy = 0.0;
+        e.ecc = p[18 * cap];
+        e.ang = p[19 * cap];
+    }
 }
 
 template <class TR>
@@ -411,8 +457,14 @@ __device__ __forceinline__ void save_event(const DevCfg& c, uint32_t slot, long 
 
 enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2 };
 
+#ifndef SG_HOT_MINB
+#define SG_HOT_MINB 4
+#endif
+#ifndef SG_CONT_MINB
+#define SG_CONT_MINB 3
+#endif
 template <class TR, typename OT>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
 hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
     constexpr int D = TR::D;
@@ -428,10 +480,11 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
     double Ax[7], Ay[7], h = 0, lx = 0, ly = 0;
     uint32_t active = 0;
 
+    EnvRegs<TR> e;
+    Act act;
     if (valid) {
-        EnvRegs<TR> e;
         load_env<TR>(c, i, e);
-        const Act act = fetch_action<TR>(c, actions, i, step0);
+        act = fetch_action<TR>(c, actions, i, step0);
         lx = e.x;
         ly = e.y;  // env.last_xy (spaceship_env.py:74)
         double g[TR::NEV], pd[TR::NP];
@@ -441,13 +494,13 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
         if (t_new - c.T > 0) t_new = c.T;
         h = t_new;
         S.h_abs = fabs(h);
-        double xn, yn, thn, vxn, vyn, omn, cn, sn, err;
-        rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err);
-        if (!controller(err, rejected, t_new < c.T, S.h_abs)) {
+        double xn, yn, thn, vxn, vyn, omn, cn, sn, err2;
+        rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
+        if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
             kind = KIND_CONT;  // rejected: the attempt loop is resumed from the same state with the smaller step
         } else {
-            double gn[TR::NEV];
-            event_values(c, e, xn, yn, omn, gn, pd);
+            double gn[TR::NEV], ipd[TR::NP];
+            event_values_inv(c, e, xn, yn, omn, gn, pd, ipd);
             active = active_events<TR>(g, gn);
             if (active) {
                 kind = KIND_EVENT;
@@ -458,7 +511,7 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
             } else {
                 uint32_t status = 0;
                 commit_state<TR>(e, xn, yn, thn, vxn, vyn, omn, status);
-                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, false, obs ? sobs + threadIdx.x * D : nullptr, cn, sn,
+                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? sobs + threadIdx.x * D : nullptr, cn, sn,
                                    reward, done_out, trunc_out, st, reached, done);
                 need_post = reached || (done && c.auto_reset);
                 if (status) c.status[i] |= status;
@@ -469,7 +522,10 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
     const uint32_t s_cont = queue_push(&c.q_counts[0], kind == KIND_CONT);
     const uint32_t s_event = queue_push(&c.q_counts[1], kind == KIND_EVENT);
     const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
-    if (kind == KIND_CONT) save_cont<TR>(c, s_cont, i, S, lx, ly, rejected);
+    if (kind == KIND_CONT) {
+        save_cont<TR>(c, c.q_cont, c.scr_cont, s_cont, i, S, lx, ly, rejected);
+        save_cont_scene<TR>(c, c.scr_cont, s_cont, e, act);
+    }
     if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
     if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
     if (obs) {
@@ -479,14 +535,105 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
     block_stats_flush<kBlock>(c, st);
 }
 
-// envs that need more than one Runge-Kutta step: resume solve_ivp's loop, densely packed
+template <class TR>
+__device__ __forceinline__ void load_cont(const DevCfg& c, const double* scr, uint32_t j, const Act& act, Integ<TR>& S,
+                                          double& lx, double& ly, bool& rejected) {
+    const long long cap = c.q_cap;
+    const double* p = scr + j;
+    S.x = p[0 * cap]; S.y = p[1 * cap]; S.th = p[2 * cap]; S.vx = p[3 * cap]; S.vy = p[4 * cap];
+    S.om = p[5 * cap]; S.cth = p[6 * cap]; S.sth = p[7 * cap]; S.Ax = p[8 * cap]; S.Ay = p[9 * cap];
+    S.h_abs = p[10 * cap]; S.t = p[11 * cap];
+    lx = p[12 * cap]; ly = p[13 * cap];
+    rejected = p[14 * cap] != 0.0;
+    S.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
+    S.fs = act.fs;
+}
+
+// Envs that need a second Runge-Kutta attempt (21 % of all): exactly ONE more attempt each, same shape and
+// register budget as the hot kernel so that it runs (and co-resides with hot blocks of other streams) at the
+// same efficiency.  The few that need yet another attempt go to the second queue (generic loop kernel).
 template <class TR, typename OT>
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
+cont1_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
+    const uint32_t count = c.q_counts[0];
+    double st[4] = {0, 0, 0, 0};
+    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
+        const uint32_t j = base + threadIdx.x;
+        const bool valid = j < count;
+        int kind = KIND_DONE;
+        bool need_post = false, reached = false, done = false, rejected = false;
+        long long i = 0;
+        Integ<TR> S;
+        EnvRegs<TR> e;
+        Act act;
+        double Ax[7], Ay[7], h = 0, lx = 0, ly = 0;
+        uint32_t active = 0;
+        if (valid) {
+            i = c.q_cont[j];
+            load_cont_scene<TR>(c, c.scr_cont, j, e, act);
+            load_cont<TR>(c, c.scr_cont, j, act, S, lx, ly, rejected);
+            double g[TR::NEV], pd[TR::NP];
+            event_values(c, e, S.x, S.y, S.om, g, pd);
+            // one pass of the attempt loop of _step_impl (scipy:rk.py:119-165)
+            const double min_step = min_step_at(S.t);
+            if (S.h_abs < min_step && !rejected) S.h_abs = min_step;
+            if (S.h_abs < min_step) {
+                kind = KIND_CONT;  // TOO_SMALL_STEP: let the generic kernel flag it
+            } else {
+                double t_new = S.t + S.h_abs;
+                if (t_new - c.T > 0) t_new = c.T;
+                h = t_new - S.t;
+                S.h_abs = fabs(h);
+                double xn, yn, thn, vxn, vyn, omn, cn, sn, err2;
+                rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
+                if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
+                    kind = KIND_CONT;
+                } else {
+                    rejected = false;
+                    double gn[TR::NEV], ipd[TR::NP];
+                    event_values_inv(c, e, xn, yn, omn, gn, pd, ipd);
+                    active = active_events<TR>(g, gn);
+                    if (active) {
+                        kind = KIND_EVENT;
+                    } else if (t_new < c.T) {
+                        kind = KIND_CONT;
+                        S.x = xn; S.y = yn; S.th = thn; S.vx = vxn; S.vy = vyn; S.om = omn;
+                        S.cth = cn; S.sth = sn; S.Ax = Ax[6]; S.Ay = Ay[6]; S.t = t_new;
+                    } else {
+                        uint32_t status = 0;
+                        commit_state<TR>(e, xn, yn, thn, vxn, vyn, omn, status);
+                        OT row[TR::D];
+                        finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? row : nullptr, cn, sn, reward,
+                                           done_out, trunc_out, st, reached, done);
+                        if (obs) {
+#pragma unroll
+                            for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
+                        }
+                        need_post = reached || (done && c.auto_reset);
+                        if (status) c.status[i] |= status;
+                    }
+                }
+            }
+        }
+        const uint32_t s_cont = queue_push(&c.q_counts[6], kind == KIND_CONT);
+        const uint32_t s_event = queue_push(&c.q_counts[1], kind == KIND_EVENT);
+        const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
+        if (kind == KIND_CONT) save_cont<TR>(c, c.q_cont2, c.scr_cont2, s_cont, i, S, lx, ly, rejected);
+        if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
+        if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
+    }
+    block_stats_flush<kBlock>(c, st);
+}
+
+// envs that still need more Runge-Kutta steps (rare): resume solve_ivp's loop until it finishes
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock, SG_CONT_MINB)
 cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
     const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
-    const uint32_t count = c.q_counts[0];
-    const long long cap = c.q_cap;
+    const uint32_t count = c.q_counts[6];
     double st[4] = {0, 0, 0, 0};
     for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
         const uint32_t j = base + threadIdx.x;
@@ -497,18 +644,12 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         EventIO<TR> io;
         double lx = 0, ly = 0;
         if (valid) {
-            i = c.q_cont[j];
+            i = c.q_cont2[j];
             EnvRegs<TR> e;
             load_env<TR>(c, i, e);
             const Act act = fetch_action<TR>(c, actions, i, step0);
-            const double* p = c.scr_cont + j;
-            S.x = p[0 * cap]; S.y = p[1 * cap]; S.th = p[2 * cap]; S.vx = p[3 * cap]; S.vy = p[4 * cap];
-            S.om = p[5 * cap]; S.cth = p[6 * cap]; S.sth = p[7 * cap]; S.Ax = p[8 * cap]; S.Ay = p[9 * cap];
-            S.h_abs = p[10 * cap]; S.t = p[11 * cap];
-            lx = p[12 * cap]; ly = p[13 * cap];
-            const bool rejected = p[14 * cap] != 0.0;
-            S.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
-            S.fs = act.fs;
+            bool rejected;
+            load_cont<TR>(c, c.scr_cont2, j, act, S, lx, ly, rejected);
             double g[TR::NEV], pd[TR::NP];
             event_values(c, e, S.x, S.y, S.om, g, pd);
             const int rc = rk_loop<TR>(c, e, S, g, rejected, &io, pd);
@@ -518,8 +659,11 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
                 uint32_t status = (rc == RK_FAILED) ? 1u : 0u;
                 commit_state<TR>(e, S.x, S.y, S.th, S.vx, S.vy, S.om, status);
                 OT row[TR::D];
-                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, false, obs ? row : nullptr, S.cth, S.sth, reward, done_out,
-                                   trunc_out, st, reached, done);
+                double ipd[TR::NP];
+#pragma unroll
+                for (int q = 0; q < TR::NP; ++q) ipd[q] = fast_rcp(pd[q]);
+                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? row : nullptr, S.cth, S.sth, reward,
+                                   done_out, trunc_out, st, reached, done);
                 if (obs) {
 #pragma unroll
                     for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
@@ -585,7 +729,10 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
             OT row[TR::D];
             const bool want_row = obs && !c.auto_reset;  // with auto-reset the reset observation replaces it
             bool reached, done;
-            finish_env<TR, OT>(c, i, e, act, lx, ly, pd, true, want_row ? row : nullptr, cs, sn, reward, done_out,
+            double ipd[TR::NP];
+#pragma unroll
+            for (int q = 0; q < TR::NP; ++q) ipd[q] = fast_rcp(pd[q]);
+            finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, true, want_row ? row : nullptr, cs, sn, reward, done_out,
                                trunc_out, st, reached, done);
             if (want_row) {
 #pragma unroll
@@ -606,6 +753,7 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
     __syncthreads();
     if (last) {  // ... and advances the device-side step counter that keys the synthetic-action stream
         if (threadIdx.x < 4) c.q_counts[threadIdx.x] = 0;
+        if (threadIdx.x == 5) c.q_counts[6] = 0;
         if (threadIdx.x == 4) *reinterpret_cast<unsigned long long*>(c.q_counts + 4) = step0 + 1;
     }
 }
@@ -718,6 +866,11 @@ struct sg_env {
         cudaEvent_t done;
     } sub[8];
     cudaEvent_t fork_ev;
+    // the small latency-bound kernels of a step (continuation, tail) run on a high-priority stream so that
+    // their blocks are scheduled ahead of the pending hot-kernel blocks of other handles' steps
+    cudaStream_t hi_stream;
+    cudaEvent_t ev_hot, ev_tail;
+    int use_priority;
     struct GraphEntry {
         const void* key[5];
         cudaGraphExec_t exec;
@@ -906,7 +1059,8 @@ extern "C" int sg_state_layout(const sg_config* cfg, int64_t n, sg_layout* out) 
 }
 
 static size_t queue_bytes(long long n) {
-    size_t b = 256 + 3 * ((((size_t)n * 4 + 255) / 256) * 256) + (size_t)(kContFields + kEventFields) * (size_t)n * sizeof(double);
+    size_t b = 256 + 4 * ((((size_t)n * 4 + 255) / 256) * 256) +
+               (size_t)(2 * kContFields + kEventFields) * (size_t)n * sizeof(double);
     return ((b + 255) / 256) * 256;
 }
 
@@ -991,8 +1145,10 @@ static void build_dev(sg_env* h) {
         x.q_cont = (uint32_t*)(q + 256);
         x.q_event = (uint32_t*)(q + 256 + idx_bytes);
         x.q_post = (uint32_t*)(q + 256 + 2 * idx_bytes);
-        x.scr_cont = (double*)(q + 256 + 3 * idx_bytes);
+        x.q_cont2 = (uint32_t*)(q + 256 + 3 * idx_bytes);
+        x.scr_cont = (double*)(q + 256 + 4 * idx_bytes);
         x.scr_event = x.scr_cont + (size_t)kContFields * n;
+        x.scr_cont2 = x.scr_event + (size_t)kEventFields * n;
         x.q_cap = sb.n;
         q += queue_bytes(sb.n);
     }
@@ -1026,6 +1182,9 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     h->n_graphs = 0;
     h->graph_clock = 0;
     h->fork_ev = nullptr;
+    h->hi_stream = nullptr;
+    h->ev_hot = h->ev_tail = nullptr;
+    h->use_priority = 0;
     memset(h->sub, 0, sizeof(h->sub));
     memset(h->graphs, 0, sizeof(h->graphs));
     h->hstream = nullptr;
@@ -1070,6 +1229,15 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
             if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->sub[s].done, cudaEventDisableTiming);
         }
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
+        const char* env_pri = getenv("SG_PRIORITY");
+        h->use_priority = env_pri ? atoi(env_pri) : 0;
+        if (err == cudaSuccess) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = greatest priority
+            err = cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi);
+            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->ev_hot, cudaEventDisableTiming);
+            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming);
+        }
     }
     if (err == cudaSuccess) err = cudaMemset(h->state, 0, (size_t)h->lay.total_bytes);
     if (err == cudaSuccess) err = cudaMemset(h->d_stats, 0, 4 * sizeof(double));
@@ -1107,6 +1275,9 @@ extern "C" void sg_destroy(sg_env* h) {
         if (h->sub[s].done) cudaEventDestroy(h->sub[s].done);
     }
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
+    if (h->ev_hot) cudaEventDestroy(h->ev_hot);
+    if (h->ev_tail) cudaEventDestroy(h->ev_tail);
     if (h->s_actions) cudaFree(h->s_actions);
     if (h->s_obs) cudaFree(h->s_obs);
     if (h->s_reward) cudaFree(h->s_reward);
@@ -1156,6 +1327,7 @@ struct LaunchArgs {
     const uint8_t* mask;
     double* vf_out;
     int sub;  // OP_STEP_SPLIT: sub-batch index
+    cudaStream_t hi_stream;  // OP_STEP_SPLIT: stream of the small kernels (nullptr: same stream)
 };
 
 template <class TR, typename OT>
@@ -1178,8 +1350,19 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         uint8_t* dn = a.done ? a.done + off : nullptr;
         uint8_t* tr = a.trunc ? a.trunc + off : nullptr;
         hot_kernel<TR, OT><<<hot_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
-        cont_kernel<TR, OT><<<cont_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
-        tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
+        cudaStream_t small = a.stream;
+        if (a.hi_stream) {
+            small = a.hi_stream;
+            cudaEventRecord(h->ev_hot, a.stream);
+            cudaStreamWaitEvent(small, h->ev_hot, 0);
+        }
+        cont1_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        cont_kernel<TR, OT><<<sms, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        if (a.hi_stream) {
+            cudaEventRecord(h->ev_tail, small);
+            cudaStreamWaitEvent(a.stream, h->ev_tail, 0);
+        }
     } else if (a.op == OP_RESET) {
         reset_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.mask, (OT*)a.obs);
     }
@@ -1213,7 +1396,7 @@ static int enqueue(sg_env* h, const LaunchArgs& a) {
     else if (h->cfg.n_planets == 3) launch_np<TASK_GOAL, 3>(h, a);
     else if (h->cfg.n_planets == 4) launch_np<TASK_GOAL, 4>(h, a);
     else return fail(h, SG_ERR_INVALID, "unsupported n_planets");
-    h->launches += (a.op == OP_STEP_SPLIT) ? 3 : 1;
+    h->launches += (a.op == OP_STEP_SPLIT) ? 4 : 1;
     return SG_OK;
 }
 
@@ -1232,8 +1415,10 @@ static int enqueue_split_step(sg_env* h, cudaStream_t origin, LaunchArgs a) {
     if (h->n_sub == 1) {
         a.sub = 0;
         a.stream = origin;
+        a.hi_stream = (h->use_priority == 1 && origin != h->hi_stream) ? h->hi_stream : nullptr;
         return enqueue(h, a);
     }
+    a.hi_stream = nullptr;
     SG_CUDA(h, cudaEventRecord(h->fork_ev, origin));
     for (int s = 0; s < h->n_sub; ++s) {
         cudaStream_t st = h->sub[s].stream;
@@ -1255,7 +1440,7 @@ static int enqueue_split_step(sg_env* h, cudaStream_t origin, LaunchArgs a) {
 // Same, replayed from a cached CUDA graph keyed by the argument pointers (one launch per env step).
 static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a) {
     SG_CUDA(h, cudaSetDevice(h->device));
-    if (h->n_sub == 1 || !h->use_graphs) {
+    if (!h->use_graphs || h->n_sub == 1) {  // graph replay of the 4-kernel chain measured slower than plain launches
         int rc = enqueue_split_step(h, user, a);
         if (rc != SG_OK) return rc;
         SG_CUDA(h, cudaGetLastError());
@@ -1266,7 +1451,8 @@ static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a) 
     for (int g = 0; g < h->n_graphs; ++g)
         if (!memcmp(h->graphs[g].key, key, sizeof(key))) hit = &h->graphs[g];
     if (!hit) {
-        cudaStream_t origin = h->sub[0].stream;  // capture is not allowed on the legacy default stream
+        // capture is not allowed on the legacy default stream: capture on an internal one
+        cudaStream_t origin = h->n_sub > 1 ? h->sub[0].stream : h->hi_stream;
         cudaGraph_t graph = nullptr;
         const int64_t launches_before = h->launches;
         SG_CUDA(h, cudaStreamBeginCapture(origin, cudaStreamCaptureModeRelaxed));
@@ -1296,7 +1482,7 @@ static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a) 
     }
     hit->stamp = ++h->graph_clock;
     SG_CUDA(h, cudaGraphLaunch(hit->exec, user));
-    h->launches += 3 * h->n_sub;
+    h->launches += 4 * h->n_sub;
     return SG_OK;
 }
 
