@@ -38,7 +38,7 @@ EXPORTS = [
     "sg_config_from_id", "sg_config_finalize", "sg_obs_dim", "sg_state_layout", "sg_create", "sg_destroy",
     "sg_last_error", "sg_get_layout", "sg_state_ptr", "sg_reset", "sg_step", "sg_reset_host", "sg_step_host", "sg_step_host_async", "sg_host_wait",
     "sg_vector_field", "sg_stats", "sg_stats_reset", "sg_step_count", "sg_set_step_count", "sg_kernel_launches",
-    "sg_measure_fp64_peak", "sg_version",
+    "sg_measure_fp64_peak", "sg_version", "sg_debug_kernel_times",
 ]
 
 _lib = None
@@ -81,6 +81,7 @@ def lib():
     L.sg_set_step_count.argtypes = [vp, C.c_uint64]
     L.sg_kernel_launches.argtypes = [vp]
     L.sg_kernel_launches.restype = C.c_int64
+    L.sg_debug_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     L.sg_measure_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double)]
     L.sg_version.restype = C.c_char_p
     _lib = L

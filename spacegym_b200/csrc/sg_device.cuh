@@ -381,22 +381,38 @@ struct Dense {  // scipy:rk.py:715-737, specialised: heading and its rate are ex
         om = om0 + alpha * dt;
         th = th0 + om0 * dt + 0.5 * alpha * dt * dt;
     }
+    // what the event functions look at: position and heading rate
+    __device__ void eval_xyo(double t, double& x, double& y, double& om) const {
+        double s = (t - t_old) / h;
+        double s2 = s * s, s3 = s2 * s, s4 = s3 * s;
+        x = x0 + h * (Qx[0] * s + Qx[1] * s2 + Qx[2] * s3 + Qx[3] * s4);
+        y = y0 + h * (Qy[0] * s + Qy[1] * s2 + Qy[2] * s3 + Qy[3] * s4);
+        om = om0 + alpha * (t - t_old);
+    }
 };
 
+// value of event `ev` at time t of the accepted step; `ev` may differ from lane to lane, so the selection of
+// the planet and of the event kind is done with selects instead of indexed (local-memory) accesses
 template <class TR>
 __device__ double event_at(const DevCfg& c, const EventIO<TR>& io, const Dense<TR>& d, int ev, double t) {
-    double x, y, th, vx, vy, om;
-    d.eval(t, x, y, th, vx, vy, om);
+    double x, y, om;
+    d.eval_xyo(t, x, y, om);
     constexpr int NPL = TR::NEV - 3;  // planet-type events
-    if (ev < NPL) {
-        int p = (TR::TASK == TASK_GOAL) ? ev : 0;
-        double dx = io.px[p] - x, dy = io.py[p] - y;
-        double r = (TR::TASK == TASK_GOAL) ? c.r0 : (ev == 0 ? c.r0 : c.r1);
-        return sqrt(dx * dx + dy * dy) - r;
+    double pxs = io.px[0], pys = io.py[0];
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int p = 1; p < TR::NP; ++p) {
+            pxs = (ev == p) ? io.px[p] : pxs;
+            pys = (ev == p) ? io.py[p] : pys;
+        }
     }
-    if (ev == NPL) return fmin(c.half_ws - x, c.half_ws - y);
-    if (ev == NPL + 1) return fmin(c.half_ws + x, c.half_ws + y);
-    return c.om_max - fabs(om);
+    const double r = (TR::TASK == TASK_GOAL) ? c.r0 : (ev == 0 ? c.r0 : c.r1);
+    const double dx = pxs - x, dy = pys - y;
+    const double g_planet = sqrt(dx * dx + dy * dy) - r;
+    const double g_max = fmin(c.half_ws - x, c.half_ws - y);
+    const double g_min = fmin(c.half_ws + x, c.half_ws + y);
+    const double g_om = c.om_max - fabs(om);
+    return ev < NPL ? g_planet : (ev == NPL ? g_max : (ev == NPL + 1 ? g_min : g_om));
 }
 
 // Brent's method as scipy.optimize.brentq runs it from scipy:ivp.py:52-77 (xtol = rtol = 4 eps,
@@ -497,8 +513,10 @@ __device__ __noinline__ void handle_events(const DevCfg& c, EventIO<TR>* io) {
     }
     double best = INFINITY;
     uint32_t status = 0;
-    for (int ev = 0; ev < TR::NEV; ++ev) {
-        if (!((io->active >> ev) & 1u)) continue;
+    // every lane walks its OWN active events (usually one): the warp makes max-popcount passes through Brent's
+    // method instead of one pass per event kind that any lane has active
+    for (uint32_t mask = io->active; mask; mask &= mask - 1u) {
+        const int ev = __ffs((int)mask) - 1;
         double root = brent_root(c, *io, d, ev, io->t_old, io->t_old + io->h, status);
         if (root < best) best = root;
     }
@@ -980,13 +998,20 @@ __device__ __forceinline__ double kepler_reward(const DevCfg& c, const EnvRegs<T
 // ---- hexagonal tiling state (hexagonal_tiling.py) ---------------------------------------------------------
 struct Tiles {
     uint32_t case_b, flip_xy, ship_tile, goal_tile, n_free;  // goal_tile 63 = None
-    unsigned long long fw[4];                                // free multiset, 4 bits per entry
-    double cs[4];                                            // column shifts
-    __device__ uint32_t get(uint32_t k) const { return (uint32_t)(fw[k >> 4] >> ((k & 15u) * 4u)) & 15u; }
+    unsigned long long fw0, fw1, fw2, fw3;                   // free multiset, 4 bits per entry (registers, no indexing)
+    double cs0, cs1, cs2, cs3;                               // column shifts
+    __device__ unsigned long long word(uint32_t w) const { return w == 0 ? fw0 : (w == 1 ? fw1 : (w == 2 ? fw2 : fw3)); }
+    __device__ uint32_t get(uint32_t k) const { return (uint32_t)(word(k >> 4) >> ((k & 15u) * 4u)) & 15u; }
     __device__ void set(uint32_t k, uint32_t v) {
-        unsigned long long m = 15ull << ((k & 15u) * 4u);
-        fw[k >> 4] = (fw[k >> 4] & ~m) | ((unsigned long long)v << ((k & 15u) * 4u));
+        const uint32_t w = k >> 4, sh = (k & 15u) * 4u;
+        const unsigned long long m = 15ull << sh;
+        const unsigned long long nw = (word(w) & ~m) | ((unsigned long long)v << sh);
+        fw0 = (w == 0) ? nw : fw0;
+        fw1 = (w == 1) ? nw : fw1;
+        fw2 = (w == 2) ? nw : fw2;
+        fw3 = (w == 3) ? nw : fw3;
     }
+    __device__ double shift(int col) const { return col == 0 ? cs0 : (col == 1 ? cs1 : (col == 2 ? cs2 : cs3)); }
     __device__ uint32_t pack() const {
         return case_b | (flip_xy << 1) | (ship_tile << 2) | (goal_tile << 8) | (n_free << 14);
     }
@@ -998,14 +1023,27 @@ struct Tiles {
 
 __device__ inline void load_tiles(const DevCfg& c, long long i, Tiles& t) {
     t.unpack(c.tile_word[i]);
-    for (int k = 0; k < 4; ++k) t.fw[k] = c.free_tiles[k * c.stride + i];
-    for (int k = 0; k < c.cols; ++k) t.cs[k] = c.col_shift[k * c.stride + i];
+    t.fw0 = c.free_tiles[i];
+    t.fw1 = c.free_tiles[c.stride + i];
+    t.fw2 = c.free_tiles[2 * c.stride + i];
+    t.fw3 = c.free_tiles[3 * c.stride + i];
+    t.cs0 = c.col_shift[i];
+    t.cs1 = c.cols > 1 ? c.col_shift[c.stride + i] : 0.0;
+    t.cs2 = c.cols > 2 ? c.col_shift[2 * c.stride + i] : 0.0;
+    t.cs3 = c.cols > 3 ? c.col_shift[3 * c.stride + i] : 0.0;
 }
 __device__ inline void store_tiles(const DevCfg& c, long long i, const Tiles& t, bool with_shift) {
     c.tile_word[i] = t.pack();
-    for (int k = 0; k < 4; ++k) c.free_tiles[k * c.stride + i] = t.fw[k];
-    if (with_shift)
-        for (int k = 0; k < c.cols; ++k) c.col_shift[k * c.stride + i] = t.cs[k];
+    c.free_tiles[i] = t.fw0;
+    c.free_tiles[c.stride + i] = t.fw1;
+    c.free_tiles[2 * c.stride + i] = t.fw2;
+    c.free_tiles[3 * c.stride + i] = t.fw3;
+    if (with_shift) {
+        c.col_shift[i] = t.cs0;
+        if (c.cols > 1) c.col_shift[c.stride + i] = t.cs1;
+        if (c.cols > 2) c.col_shift[2 * c.stride + i] = t.cs2;
+        if (c.cols > 3) c.col_shift[3 * c.stride + i] = t.cs3;
+    }
 }
 
 // HexagonalTiling._tile_center_pos (hexagonal_tiling.py:136-158)
@@ -1014,7 +1052,7 @@ __device__ inline void tile_center(const DevCfg& c, const Tiles& t, int tile, do
     double zero_x = -c.ws / 2 + c.hex_width / 2;
     double zero_y = c.ws / 2 - c.hex_height / 2;
     if (t.case_b) zero_y -= c.hex_height / 2;
-    double x_shift = col * 1.5 * c.hex_a + t.cs[col];
+    double x_shift = col * 1.5 * c.hex_a + t.shift(col);
     double y_rows = -row * c.hex_height;
     double y_cols = -(col % 2) * c.hex_height / 2;
     if (t.case_b) y_cols *= -1;
@@ -1023,17 +1061,37 @@ __device__ inline void tile_center(const DevCfg& c, const Tiles& t, int tile, do
     oy = t.flip_xy ? cx : cy;
 }
 
-// choice(n, size=k, replace=False) as a partial Fisher-Yates (uniform ordered k-subset)
-__device__ inline void choice_no_replace(Rng& rng, int n, int k, int* out) {
+// choice(n, size=k, replace=False) as a partial Fisher-Yates (uniform ordered k-subset).  For n <= 16 the
+// permutation lives in one 64-bit register, 4 bits per element; longer free lists (rare) use a local array.
+template <int KMAX>
+__device__ inline void choice_no_replace(Rng& rng, int n, int k, int (&out)[KMAX]) {
+    if (n <= 16) {
+        unsigned long long perm = 0xFEDCBA9876543210ull;
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) {
+            if (i < k) {
+                int j = i + (int)(rng.uniform() * (n - i));
+                if (j > n - 1) j = n - 1;
+                const unsigned long long ai = (perm >> (4 * i)) & 15ull, aj = (perm >> (4 * j)) & 15ull;
+                const unsigned long long dx = ai ^ aj;
+                perm ^= (dx << (4 * i)) | (dx << (4 * j));  // swap the two nibbles (no-op when i == j)
+                out[i] = (int)aj;
+            }
+        }
+        return;
+    }
     int arr[64];
     for (int i = 0; i < n; ++i) arr[i] = i;
-    for (int i = 0; i < k; ++i) {
-        int j = i + (int)(rng.uniform() * (n - i));
-        if (j > n - 1) j = n - 1;
-        int tmp = arr[i];
-        arr[i] = arr[j];
-        arr[j] = tmp;
-        out[i] = arr[i];
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+        if (i < k) {
+            int j = i + (int)(rng.uniform() * (n - i));
+            if (j > n - 1) j = n - 1;
+            int tmp = arr[i];
+            arr[i] = arr[j];
+            arr[j] = tmp;
+            out[i] = arr[i];
+        }
     }
 }
 
@@ -1053,15 +1111,18 @@ __device__ inline void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double
     } else {
         int k = t.n_free < 3u ? (int)t.n_free : 3;
         int cand[3];
-        choice_no_replace(rng, (int)t.n_free, k, cand);
+        choice_no_replace<3>(rng, (int)t.n_free, k, cand);
         int best = -1, best_idx = 0;
         int srow = (int)t.ship_tile / c.cols, scol = (int)t.ship_tile % c.cols;
-        for (int i = 0; i < k; ++i) {
-            int tnr = (int)t.get((uint32_t)cand[i]);
-            int taxi = abs(tnr / c.cols - srow) + abs(tnr % c.cols - scol);
-            if (taxi > best) {
-                best = taxi;
-                best_idx = cand[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (i < k) {
+                int tnr = (int)t.get((uint32_t)cand[i]);
+                int taxi = abs(tnr / c.cols - srow) + abs(tnr % c.cols - scol);
+                if (taxi > best) {
+                    best = taxi;
+                    best_idx = cand[i];
+                }
             }
         }
         t.goal_tile = t.get((uint32_t)best_idx);
@@ -1099,20 +1160,25 @@ __device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, 
         constexpr int P = TR::NP;
         const int n_tiles = c.rows * c.cols;
         Tiles t;
-        for (int k = 0; k < 4; ++k) {
-            t.fw[k] = 0;
-            t.cs[k] = 0;
-        }
+        t.fw0 = t.fw1 = t.fw2 = t.fw3 = 0;
         t.goal_tile = 63u;
         t.case_b = rng.uniform() < 0.5;
         t.flip_xy = rng.uniform() < 0.5;
-        double acc = 0;
-        for (int k = 0; k < c.cols; ++k) {
+        double acc = rng.uniform();  // cumsum of `cols` uniforms (cols >= 2), rescaled so the last one is free_x
+        t.cs0 = acc;
+        acc += rng.uniform();
+        t.cs1 = acc;
+        t.cs2 = t.cs3 = 0.0;
+        if (c.cols > 2) {
             acc += rng.uniform();
-            t.cs[k] = acc;
+            t.cs2 = acc;
         }
-        double sc = c.free_x / t.cs[c.cols - 1];
-        for (int k = 0; k < c.cols; ++k) t.cs[k] *= sc;
+        if (c.cols > 3) {
+            acc += rng.uniform();
+            t.cs3 = acc;
+        }
+        const double sc = c.free_x / acc;
+        t.cs0 *= sc; t.cs1 *= sc; t.cs2 *= sc; t.cs3 *= sc;
         int tiles[P + 1];
         bool diag = false;
         if (P == 2) diag = rng.uniform() < 0.25;
@@ -1122,7 +1188,7 @@ __device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, 
             if (k > 3) k = 3;
             for (int j = 0; j < 3 && j < P + 1; ++j) tiles[j] = cases[k][j];
         } else {
-            choice_no_replace(rng, n_tiles, P + 1, tiles);
+            choice_no_replace<P + 1>(rng, n_tiles, P + 1, tiles);
         }
         t.ship_tile = (uint32_t)tiles[0];
         t.n_free = 0;

@@ -259,6 +259,15 @@ constexpr int kContFields = 28;   // x y th vx vy om cth sth Ax Ay h_abs t lx ly
 constexpr int kEventFields = 25;  // x y th vx vy om h t_old Ax[7] Ay[7] lx ly active
 constexpr uint32_t kPostReached = 1u << 30, kPostDone = 1u << 31, kPostIndex = (1u << 30) - 1;
 
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // warp-aggregated queue append; must be called by all 32 lanes of the warp
 __device__ __forceinline__ uint32_t queue_push(uint32_t* counter, bool need) {
     const unsigned mask = __ballot_sync(0xffffffffu, need);
@@ -268,6 +277,24 @@ __device__ __forceinline__ uint32_t queue_push(uint32_t* counter, bool need) {
     if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// three appends at once: lane 0 issues the (up to) three atomics back to back, so their L2 round trips overlap
+__device__ __forceinline__ void queue_push3(uint32_t* c0, bool n0, uint32_t* c1, bool n1, uint32_t* c2, bool n2,
+                                            uint32_t& s0, uint32_t& s1, uint32_t& s2) {
+    const unsigned m0 = __ballot_sync(0xffffffffu, n0), m1 = __ballot_sync(0xffffffffu, n1),
+                   m2 = __ballot_sync(0xffffffffu, n2);
+    const int lane = threadIdx.x & 31;
+    uint32_t b0 = 0, b1 = 0, b2 = 0;
+    if (lane == 0) {
+        if (m0) b0 = atomicAdd(c0, (uint32_t)__popc(m0));
+        if (m1) b1 = atomicAdd(c1, (uint32_t)__popc(m1));
+        if (m2) b2 = atomicAdd(c2, (uint32_t)__popc(m2));
+    }
+    const unsigned below = (1u << lane) - 1u;
+    s0 = __shfl_sync(0xffffffffu, b0, 0) + (uint32_t)__popc(m0 & below);
+    s1 = __shfl_sync(0xffffffffu, b1, 0) + (uint32_t)__popc(m1 & below);
+    s2 = __shfl_sync(0xffffffffu, b2, 0) + (uint32_t)__popc(m2 & below);
 }
 
 template <int BLOCK>
@@ -307,9 +334,9 @@ __device__ __forceinline__ Act fetch_action(const DevCfg& c, const float* __rest
 template <class TR, typename OT>
 __device__ __forceinline__ void finish_env(const DevCfg& c, long long i, EnvRegs<TR>& e, const Act& act, double lx,
                                            double ly, const double (&pd)[TR::NP], const double (&ipd)[TR::NP], bool dn,
-                                           OT* obs_row, double cs, double sn, double* __restrict__ reward,
-                                           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
-                                           double (&st)[4], bool& reached, bool& done) {
+                                           OT* obs_row, double cs, double sn, uint32_t elapsed0, double ep_ret0,
+                                           double* __restrict__ reward, uint8_t* __restrict__ done_out,
+                                           uint8_t* __restrict__ trunc_out, double (&st)[4], bool& reached, bool& done) {
     if (obs_row) make_obs_inv<TR, OT>(c, e, cs, sn, ipd, obs_row);
     double r;
     reached = false;
@@ -324,13 +351,13 @@ __device__ __forceinline__ void finish_env(const DevCfg& c, long long i, EnvRegs
     } else {
         r = kepler_reward<TR>(c, e, act);
     }
-    uint32_t elapsed = c.elapsed[i] + 1;
+    uint32_t elapsed = elapsed0 + 1;
     bool trunc = false;
     if (c.max_episode_steps > 0 && elapsed >= (uint32_t)c.max_episode_steps) {  // gym TimeLimit
         trunc = !dn;
         dn = true;
     }
-    const double ep_ret = c.ep_return[i] + r;
+    const double ep_ret = ep_ret0 + r;
     if (dn) {
         st[0] += ep_ret;
         st[1] += (double)elapsed;
@@ -383,10 +410,11 @@ __device__ __forceinline__ void post_env(const DevCfg& c, long long i, bool reac
 
 template <class TR>
 __device__ __forceinline__ void save_cont(const DevCfg& c, uint32_t* q_idx, double* scr, uint32_t slot, long long i,
-                                          const Integ<TR>& S, double lx, double ly, bool rejected) {
+                                          const Integ<TR>& S, double lx, double ly, bool rejected,
+                                          bool write_index = true) {
     const long long cap = c.q_cap;
     double* p = scr + slot;
-    q_idx[slot] = (uint32_t)i;
+    if (write_index) q_idx[slot] = (uint32_t)i;
     p[0 * cap] = S.x; p[1 * cap] = S.y; p[2 * cap] = S.th; p[3 * cap] = S.vx; p[4 * cap] = S.vy; p[5 * cap] = S.om;
     p[6 * cap] = S.cth; p[7 * cap] = S.sth; p[8 * cap] = S.Ax; p[9 * cap] = S.Ay; p[10 * cap] = S.h_abs;
     p[11 * cap] = S.t; p[12 * cap] = lx; p[13 * cap] = ly; p[14 * cap] = rejected ? 1.0 : 0.0;
@@ -463,17 +491,16 @@ enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2 };
 #ifndef SG_CONT_MINB
 #define SG_CONT_MINB 3
 #endif
+// One chunk of kBlock envs through the common path.  `publish` = true (fused persistent kernel): a
+// continuation entry becomes visible to the in-kernel consumers by the release of its index word.
 template <class TR, typename OT>
-__global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
-hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
-           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+__device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restrict__ actions, unsigned long long step0,
+                                          OT* __restrict__ obs, double* __restrict__ reward,
+                                          uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
+                                          long long block_first, OT* sobs, double (&st)[4], bool publish) {
     constexpr int D = TR::D;
-    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
-    __shared__ __align__(16) OT sobs[kBlock * D];
-    const long long block_first = (long long)blockIdx.x * kBlock;
     const long long i = block_first + threadIdx.x;
     const bool valid = i < c.n;
-    double st[4] = {0, 0, 0, 0};
     int kind = KIND_DONE;
     bool need_post = false, reached = false, done = false, rejected = false;
     Integ<TR> S;
@@ -485,6 +512,8 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
     if (valid) {
         load_env<TR>(c, i, e);
         act = fetch_action<TR>(c, actions, i, step0);
+        const uint32_t elapsed0 = c.elapsed[i];  // fetched with the state: not on the critical path of the epilogue
+        const double ep_ret0 = c.ep_return[i];
         lx = e.x;
         ly = e.y;  // env.last_xy (spaceship_env.py:74)
         double g[TR::NEV], pd[TR::NP];
@@ -512,19 +541,20 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
                 uint32_t status = 0;
                 commit_state<TR>(e, xn, yn, thn, vxn, vyn, omn, status);
                 finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? sobs + threadIdx.x * D : nullptr, cn, sn,
-                                   reward, done_out, trunc_out, st, reached, done);
+                                   elapsed0, ep_ret0, reward, done_out, trunc_out, st, reached, done);
                 need_post = reached || (done && c.auto_reset);
                 if (status) c.status[i] |= status;
             }
         }
     }
     // queue appends at warp-converged points
-    const uint32_t s_cont = queue_push(&c.q_counts[0], kind == KIND_CONT);
-    const uint32_t s_event = queue_push(&c.q_counts[1], kind == KIND_EVENT);
-    const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
+    uint32_t s_cont, s_event, s_post;
+    queue_push3(&c.q_counts[0], kind == KIND_CONT, &c.q_counts[1], kind == KIND_EVENT, &c.q_counts[2], need_post, s_cont,
+                s_event, s_post);
     if (kind == KIND_CONT) {
-        save_cont<TR>(c, c.q_cont, c.scr_cont, s_cont, i, S, lx, ly, rejected);
+        save_cont<TR>(c, c.q_cont, c.scr_cont, s_cont, i, S, lx, ly, rejected, !publish);
         save_cont_scene<TR>(c, c.scr_cont, s_cont, e, act);
+        if (publish) st_release(c.q_cont + s_cont, (uint32_t)i);  // scratch row visible before "ready"
     }
     if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
     if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
@@ -532,6 +562,16 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
         __syncthreads();
         flush_obs<OT, D>(sobs, obs, block_first, c.n);  // rows of queued envs are rewritten by the later kernels
     }
+}
+
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
+hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
+    __shared__ __align__(16) OT sobs[kBlock * TR::D];
+    double st[4] = {0, 0, 0, 0};
+    hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)blockIdx.x * kBlock, sobs, st, false);
     block_stats_flush<kBlock>(c, st);
 }
 
@@ -549,80 +589,142 @@ __device__ __forceinline__ void load_cont(const DevCfg& c, const double* scr, ui
     S.fs = act.fs;
 }
 
-// Envs that need a second Runge-Kutta attempt (21 % of all): exactly ONE more attempt each, same shape and
-// register budget as the hot kernel so that it runs (and co-resides with hot blocks of other streams) at the
-// same efficiency.  The few that need yet another attempt go to the second queue (generic loop kernel).
+// One more Runge-Kutta attempt for continuation entry j of the first queue (valid = the entry exists).
+// Same shape and register budget as the hot path.  Envs that need yet another attempt go to the second
+// queue (generic loop kernel).
+template <class TR, typename OT>
+__device__ __forceinline__ void cont1_entry(const DevCfg& c, uint32_t j, bool valid, long long i, OT* __restrict__ obs,
+                                            double* __restrict__ reward, uint8_t* __restrict__ done_out,
+                                            uint8_t* __restrict__ trunc_out, double (&st)[4]) {
+    int kind = KIND_DONE;
+    bool need_post = false, reached = false, done = false, rejected = false;
+    Integ<TR> S;
+    EnvRegs<TR> e;
+    Act act;
+    double Ax[7], Ay[7], h = 0, lx = 0, ly = 0;
+    uint32_t active = 0;
+    if (valid) {
+        const uint32_t elapsed0 = c.elapsed[i];
+        const double ep_ret0 = c.ep_return[i];
+        load_cont_scene<TR>(c, c.scr_cont, j, e, act);
+        load_cont<TR>(c, c.scr_cont, j, act, S, lx, ly, rejected);
+        double g[TR::NEV], pd[TR::NP];
+        event_values(c, e, S.x, S.y, S.om, g, pd);
+        // one pass of the attempt loop of _step_impl (scipy:rk.py:119-165)
+        const double min_step = min_step_at(S.t);
+        if (S.h_abs < min_step && !rejected) S.h_abs = min_step;
+        if (S.h_abs < min_step) {
+            kind = KIND_CONT;  // TOO_SMALL_STEP: let the generic kernel flag it
+        } else {
+            double t_new = S.t + S.h_abs;
+            if (t_new - c.T > 0) t_new = c.T;
+            h = t_new - S.t;
+            S.h_abs = fabs(h);
+            double xn, yn, thn, vxn, vyn, omn, cn, sn, err2;
+            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
+            if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
+                kind = KIND_CONT;
+            } else {
+                rejected = false;
+                double gn[TR::NEV], ipd[TR::NP];
+                event_values_inv(c, e, xn, yn, omn, gn, pd, ipd);
+                active = active_events<TR>(g, gn);
+                if (active) {
+                    kind = KIND_EVENT;
+                } else if (t_new < c.T) {
+                    kind = KIND_CONT;
+                    S.x = xn; S.y = yn; S.th = thn; S.vx = vxn; S.vy = vyn; S.om = omn;
+                    S.cth = cn; S.sth = sn; S.Ax = Ax[6]; S.Ay = Ay[6]; S.t = t_new;
+                } else {
+                    uint32_t status = 0;
+                    commit_state<TR>(e, xn, yn, thn, vxn, vyn, omn, status);
+                    OT row[TR::D];
+                    finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? row : nullptr, cn, sn, elapsed0,
+                                       ep_ret0, reward, done_out, trunc_out, st, reached, done);
+                    if (obs) {
+#pragma unroll
+                        for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
+                    }
+                    need_post = reached || (done && c.auto_reset);
+                    if (status) c.status[i] |= status;
+                }
+            }
+        }
+    }
+    uint32_t s_cont, s_event, s_post;
+    queue_push3(&c.q_counts[6], kind == KIND_CONT, &c.q_counts[1], kind == KIND_EVENT, &c.q_counts[2], need_post, s_cont,
+                s_event, s_post);
+    if (kind == KIND_CONT) save_cont<TR>(c, c.q_cont2, c.scr_cont2, s_cont, i, S, lx, ly, rejected);
+    if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
+    if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
+}
+
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
 cont1_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
              uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
-    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     const uint32_t count = c.q_counts[0];
     double st[4] = {0, 0, 0, 0};
     for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
         const uint32_t j = base + threadIdx.x;
         const bool valid = j < count;
-        int kind = KIND_DONE;
-        bool need_post = false, reached = false, done = false, rejected = false;
-        long long i = 0;
-        Integ<TR> S;
-        EnvRegs<TR> e;
-        Act act;
-        double Ax[7], Ay[7], h = 0, lx = 0, ly = 0;
-        uint32_t active = 0;
-        if (valid) {
-            i = c.q_cont[j];
-            load_cont_scene<TR>(c, c.scr_cont, j, e, act);
-            load_cont<TR>(c, c.scr_cont, j, act, S, lx, ly, rejected);
-            double g[TR::NEV], pd[TR::NP];
-            event_values(c, e, S.x, S.y, S.om, g, pd);
-            // one pass of the attempt loop of _step_impl (scipy:rk.py:119-165)
-            const double min_step = min_step_at(S.t);
-            if (S.h_abs < min_step && !rejected) S.h_abs = min_step;
-            if (S.h_abs < min_step) {
-                kind = KIND_CONT;  // TOO_SMALL_STEP: let the generic kernel flag it
-            } else {
-                double t_new = S.t + S.h_abs;
-                if (t_new - c.T > 0) t_new = c.T;
-                h = t_new - S.t;
-                S.h_abs = fabs(h);
-                double xn, yn, thn, vxn, vyn, omn, cn, sn, err2;
-                rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
-                if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
-                    kind = KIND_CONT;
-                } else {
-                    rejected = false;
-                    double gn[TR::NEV], ipd[TR::NP];
-                    event_values_inv(c, e, xn, yn, omn, gn, pd, ipd);
-                    active = active_events<TR>(g, gn);
-                    if (active) {
-                        kind = KIND_EVENT;
-                    } else if (t_new < c.T) {
-                        kind = KIND_CONT;
-                        S.x = xn; S.y = yn; S.th = thn; S.vx = vxn; S.vy = vyn; S.om = omn;
-                        S.cth = cn; S.sth = sn; S.Ax = Ax[6]; S.Ay = Ay[6]; S.t = t_new;
-                    } else {
-                        uint32_t status = 0;
-                        commit_state<TR>(e, xn, yn, thn, vxn, vyn, omn, status);
-                        OT row[TR::D];
-                        finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? row : nullptr, cn, sn, reward,
-                                           done_out, trunc_out, st, reached, done);
-                        if (obs) {
-#pragma unroll
-                            for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
-                        }
-                        need_post = reached || (done && c.auto_reset);
-                        if (status) c.status[i] |= status;
-                    }
+        const long long i = valid ? (long long)c.q_cont[j] : 0;
+        cont1_entry<TR, OT>(c, j, valid, i, obs, reward, done_out, trunc_out, st);
+    }
+    block_stats_flush<kBlock>(c, st);
+}
+
+// Fused persistent form of hot_kernel + cont1_kernel (default).  gridDim = resident CTAs.  Phase 1: CTAs pull
+// chunks of kBlock envs from a ticket counter and run the common path.  Phase 2: CTAs that run out of chunks
+// pull batches of continuation entries — written by any CTA of this launch, published by the release of the
+// entry's index word — so the second attempts fill the partial last wave of the grid instead of a separate,
+// poorly occupied launch.  A CTA only ever waits for entries of chunks that a RUNNING CTA has claimed.
+constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
+fused_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out, uint32_t n_chunks) {
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
+    __shared__ __align__(16) OT sobs[kBlock * TR::D];
+    __shared__ uint32_t s_ticket;
+    double st[4] = {0, 0, 0, 0};
+    for (;;) {  // phase 1
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&c.q_counts[7], 1u);
+        __syncthreads();
+        const uint32_t chunk = s_ticket;
+        __syncthreads();
+        if (chunk >= n_chunks) break;
+        hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)chunk * kBlock, sobs, st, true);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&c.q_counts[8], 1u);  // chunks whose entries are all published
+        }
+    }
+    uint32_t* q_idx = c.q_cont;
+    const uint32_t* chunks_done = c.q_counts + 8;
+    for (;;) {  // phase 2
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&c.q_counts[9], 1u);
+        __syncthreads();
+        const uint32_t batch = s_ticket;
+        __syncthreads();
+        const unsigned long long j64 = (unsigned long long)batch * kBlock + threadIdx.x;
+        uint32_t i = kEmptySlot;
+        if (j64 < (unsigned long long)c.q_cap) {
+            for (;;) {
+                i = ld_acquire(q_idx + j64);
+                if (i != kEmptySlot) break;
+                if (ld_acquire(chunks_done) >= n_chunks) {  // every producer has published: re-read once
+                    i = ld_acquire(q_idx + j64);
+                    break;
                 }
+                __nanosleep(64);
             }
         }
-        const uint32_t s_cont = queue_push(&c.q_counts[6], kind == KIND_CONT);
-        const uint32_t s_event = queue_push(&c.q_counts[1], kind == KIND_EVENT);
-        const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
-        if (kind == KIND_CONT) save_cont<TR>(c, c.q_cont2, c.scr_cont2, s_cont, i, S, lx, ly, rejected);
-        if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
-        if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
+        const bool have = (i != kEmptySlot);
+        if (!__syncthreads_or(have ? 1 : 0)) break;  // entries are dense: an empty batch is past the end
+        if (have) q_idx[j64] = kEmptySlot;           // leave the queue empty for the next step
+        cont1_entry<TR, OT>(c, (uint32_t)j64, have, (long long)i, obs, reward, done_out, trunc_out, st);
     }
     block_stats_flush<kBlock>(c, st);
 }
@@ -631,9 +733,11 @@ cont1_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock, SG_CONT_MINB)
 cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
-            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out, int second_queue) {
     const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
-    const uint32_t count = c.q_counts[6];
+    const uint32_t count = second_queue ? c.q_counts[6] : c.q_counts[0];
+    const uint32_t* q_in = second_queue ? c.q_cont2 : c.q_cont;
+    const double* scr_in = second_queue ? c.scr_cont2 : c.scr_cont;
     double st[4] = {0, 0, 0, 0};
     for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
         const uint32_t j = base + threadIdx.x;
@@ -644,12 +748,14 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         EventIO<TR> io;
         double lx = 0, ly = 0;
         if (valid) {
-            i = c.q_cont2[j];
+            i = q_in[j];
             EnvRegs<TR> e;
             load_env<TR>(c, i, e);
             const Act act = fetch_action<TR>(c, actions, i, step0);
             bool rejected;
-            load_cont<TR>(c, c.scr_cont2, j, act, S, lx, ly, rejected);
+            const uint32_t elapsed0 = c.elapsed[i];
+            const double ep_ret0 = c.ep_return[i];
+            load_cont<TR>(c, scr_in, j, act, S, lx, ly, rejected);
             double g[TR::NEV], pd[TR::NP];
             event_values(c, e, S.x, S.y, S.om, g, pd);
             const int rc = rk_loop<TR>(c, e, S, g, rejected, &io, pd);
@@ -662,8 +768,8 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
                 double ipd[TR::NP];
 #pragma unroll
                 for (int q = 0; q < TR::NP; ++q) ipd[q] = fast_rcp(pd[q]);
-                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? row : nullptr, S.cth, S.sth, reward,
-                                   done_out, trunc_out, st, reached, done);
+                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? row : nullptr, S.cth, S.sth, elapsed0,
+                                   ep_ret0, reward, done_out, trunc_out, st, reached, done);
                 if (obs) {
 #pragma unroll
                     for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
@@ -672,8 +778,8 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
                 if (status) c.status[i] |= status;
             }
         }
-        const uint32_t s_event = queue_push(&c.q_counts[1], is_event);
-        const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
+        uint32_t s_unused, s_event, s_post;
+        queue_push3(&c.q_counts[6], false, &c.q_counts[1], is_event, &c.q_counts[2], need_post, s_unused, s_event, s_post);
         if (is_event) {
             Integ<TR> So;
             So.x = io.x; So.y = io.y; So.th = io.th; So.vx = io.vx; So.vy = io.vy; So.om = io.om; So.t = io.t_old;
@@ -732,8 +838,8 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
             double ipd[TR::NP];
 #pragma unroll
             for (int q = 0; q < TR::NP; ++q) ipd[q] = fast_rcp(pd[q]);
-            finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, true, want_row ? row : nullptr, cs, sn, reward, done_out,
-                               trunc_out, st, reached, done);
+            finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, true, want_row ? row : nullptr, cs, sn, c.elapsed[i],
+                               c.ep_return[i], reward, done_out, trunc_out, st, reached, done);
             if (want_row) {
 #pragma unroll
                 for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
@@ -754,6 +860,7 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
     if (last) {  // ... and advances the device-side step counter that keys the synthetic-action stream
         if (threadIdx.x < 4) c.q_counts[threadIdx.x] = 0;
         if (threadIdx.x == 5) c.q_counts[6] = 0;
+        if (threadIdx.x >= 7 && threadIdx.x <= 9) c.q_counts[threadIdx.x] = 0;
         if (threadIdx.x == 4) *reinterpret_cast<unsigned long long*>(c.q_counts + 4) = step0 + 1;
     }
 }
@@ -855,6 +962,7 @@ struct sg_env {
     bool owns_state;
     double* d_stats;
     void* d_queues;  // work queues + scratch of the split step path
+    size_t q_bytes_total;
     // split path: the envs are processed as `n_sub` independent sub-batches on internal streams, so that
     // the latency-bound continuation / tail kernels of one sub-batch overlap the hot kernel of another;
     // the whole fork / join is replayed as one CUDA graph per distinct set of argument pointers
@@ -870,7 +978,11 @@ struct sg_env {
     // their blocks are scheduled ahead of the pending hot-kernel blocks of other handles' steps
     cudaStream_t hi_stream;
     cudaEvent_t ev_hot, ev_tail;
-    int use_priority;
+    int use_priority, use_fused, use_cont1;
+    int timing;                 // SG_TIMING=1: CUDA events around every kernel of the split path
+    cudaEvent_t tev[5];
+    double t_acc[4];
+    long long t_n;
     struct GraphEntry {
         const void* key[5];
         cudaGraphExec_t exec;
@@ -1224,11 +1336,24 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
         }
         if (err == cudaSuccess) err = cudaMalloc(&h->d_queues, q_bytes);
         if (err == cudaSuccess) err = cudaMemset(h->d_queues, 0, q_bytes);
+        h->q_bytes_total = q_bytes;
         for (int s = 0; s < h->n_sub && err == cudaSuccess && h->n_sub > 1; ++s) {
             err = cudaStreamCreateWithFlags(&h->sub[s].stream, cudaStreamNonBlocking);
             if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->sub[s].done, cudaEventDisableTiming);
         }
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
+        const char* env_fused = getenv("SG_FUSED");
+        h->use_fused = env_fused ? atoi(env_fused) : 0;
+        const char* env_c1 = getenv("SG_CONT1");
+        h->use_cont1 = env_c1 ? atoi(env_c1) : 0;
+        const char* env_tm = getenv("SG_TIMING");
+        h->timing = env_tm ? atoi(env_tm) : 0;
+        h->t_n = 0;
+        for (int k = 0; k < 4; ++k) h->t_acc[k] = 0;
+        for (int k = 0; k < 5; ++k) {
+            h->tev[k] = nullptr;
+            if (h->timing && err == cudaSuccess) err = cudaEventCreate(&h->tev[k]);
+        }
         const char* env_pri = getenv("SG_PRIORITY");
         h->use_priority = env_pri ? atoi(env_pri) : 0;
         if (err == cudaSuccess) {
@@ -1247,6 +1372,8 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
         return fail(nullptr, SG_ERR_CUDA, msg);
     }
     build_dev(h);
+    for (int s = 0; s < h->n_sub; ++s)  // continuation index words start out "empty" (fused kernel protocol)
+        cudaMemset(h->sub[s].dev.q_cont, 0xFF, (size_t)h->sub[s].n * sizeof(uint32_t));
     if (c.task == SG_TASK_KEPLER) {
         int blocks = (int)((n_envs + 255) / 256);
         fill_orbit_kernel<<<blocks, 256>>>(h->dev.orbit, n_envs, c.ref_orbit_eccentricity, c.ref_orbit_angle);
@@ -1311,6 +1438,17 @@ extern "C" int sg_set_step_count(sg_env* h, uint64_t s) {
 }
 extern "C" int64_t sg_kernel_launches(const sg_env* h) { return h ? h->launches : 0; }
 
+// debugging aid (SG_TIMING=1): mean milliseconds of {hot, continuation, tail} per env step so far
+extern "C" int sg_debug_kernel_times(sg_env* h, double out[3], int reset) {
+    if (!h || !out) return SG_ERR_INVALID;
+    for (int k = 0; k < 3; ++k) out[k] = h->t_n ? h->t_acc[k] / (double)h->t_n : 0.0;
+    if (reset) {
+        h->t_n = 0;
+        for (int k = 0; k < 4; ++k) h->t_acc[k] = 0;
+    }
+    return SG_OK;
+}
+
 // ---- kernel dispatch over (task, planets, steering, action space, obs dtype) -------------------
 enum Op { OP_STEP, OP_STEP_SPLIT, OP_RESET, OP_VFIELD };
 
@@ -1349,16 +1487,40 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         double* rew = a.reward ? a.reward + off : nullptr;
         uint8_t* dn = a.done ? a.done + off : nullptr;
         uint8_t* tr = a.trunc ? a.trunc + off : nullptr;
-        hot_kernel<TR, OT><<<hot_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
+        sg_env* hm = const_cast<sg_env*>(h);
+        if (h->timing) cudaEventRecord(h->tev[0], a.stream);
+        if (h->use_fused) {
+            int fused_blocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
+            fused_kernel<TR, OT><<<fused_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
+        } else {
+            hot_kernel<TR, OT><<<hot_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
+        }
+        if (h->timing) cudaEventRecord(h->tev[1], a.stream);
         cudaStream_t small = a.stream;
         if (a.hi_stream) {
             small = a.hi_stream;
             cudaEventRecord(h->ev_hot, a.stream);
             cudaStreamWaitEvent(small, h->ev_hot, 0);
         }
-        cont1_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
-        cont_kernel<TR, OT><<<sms, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        // step_plan 0 (default): hot -> generic continuation loop -> tail.  1: hot -> single-attempt continuation
+        // -> loop for the rest -> tail.  2: fused persistent hot+continuation -> loop for the rest -> tail.
+        if (h->use_fused == 0 && h->use_cont1) cont1_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        if (h->use_fused || h->use_cont1)
+            cont_kernel<TR, OT><<<sms, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr, 1);
+        else
+            cont_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr, 0);
+        if (h->timing) cudaEventRecord(h->tev[2], small);
         tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        if (h->timing) {  // debugging aid: synchronous, never on in benchmarks
+            cudaEventRecord(h->tev[3], small);
+            cudaEventSynchronize(h->tev[3]);
+            float ms = 0;
+            for (int k = 0; k < 3; ++k) {
+                cudaEventElapsedTime(&ms, h->tev[k], h->tev[k + 1]);
+                hm->t_acc[k] += ms;
+            }
+            hm->t_n += 1;
+        }
         if (a.hi_stream) {
             cudaEventRecord(h->ev_tail, small);
             cudaStreamWaitEvent(a.stream, h->ev_tail, 0);
@@ -1396,7 +1558,7 @@ static int enqueue(sg_env* h, const LaunchArgs& a) {
     else if (h->cfg.n_planets == 3) launch_np<TASK_GOAL, 3>(h, a);
     else if (h->cfg.n_planets == 4) launch_np<TASK_GOAL, 4>(h, a);
     else return fail(h, SG_ERR_INVALID, "unsupported n_planets");
-    h->launches += (a.op == OP_STEP_SPLIT) ? 4 : 1;
+    h->launches += (a.op == OP_STEP_SPLIT) ? ((h->use_cont1 && !h->use_fused) ? 4 : 3) : 1;
     return SG_OK;
 }
 
@@ -1482,7 +1644,7 @@ static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a) 
     }
     hit->stamp = ++h->graph_clock;
     SG_CUDA(h, cudaGraphLaunch(hit->exec, user));
-    h->launches += 4 * h->n_sub;
+    h->launches += 3 * h->n_sub;
     return SG_OK;
 }
 

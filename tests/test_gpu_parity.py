@@ -256,3 +256,29 @@ def test_full_size_rollout_properties():
     frac = total_done / (200.0 * n)
     assert 0.01 < frac < 0.04  # ~2 % of random-policy steps end an episode
     env.close()
+
+
+@pytest.mark.parametrize("plan", ["SG_CONT1", "SG_FUSED", "SG_SUBBATCHES"])
+def test_alternative_step_plans_match_oracle(oracle, plan, monkeypatch):
+    """The other launch plans of the split path (single-attempt continuation kernel, fused persistent
+    hot+continuation kernel with in-kernel queue consumption, concurrent sub-batches replayed as a CUDA
+    graph) stay in lockstep with the oracle twin as well."""
+    monkeypatch.setenv(plan, "3" if plan == "SG_SUBBATCHES" else "1")
+    n, T, seed = 3000, 60, 77
+    cfg = oracle_cfg(oracle, "goal3p", max_episode_steps=25)
+    eng = oracle.Engine(cfg, n, seed=seed)
+    env = sg.make("GoalContinuous3P-v0", n, seed=seed, max_episode_steps=25, copy=False)
+    assert close(env.reset().cpu().numpy(), eng.reset()).all()
+    rng = np.random.RandomState(3)
+    diverged = 0
+    for t in range(T):
+        a = random_actions(rng, 1, n, False)
+        o_o, r_o, d_o, tr_o = eng.step(a)
+        o_d, r_d, d_d, info = env.step(to_dev(a[0]))
+        ok = close(o_d.cpu().numpy(), o_o).all(axis=1) & close(r_d.cpu().numpy(), r_o[0])
+        ok &= (d_d.cpu().numpy() == d_o[0].astype(bool)) & compare_engine_to_oracle(cfg, env.get_state(), eng.envs)
+        if (~ok).any():
+            diverged += int((~ok).sum())
+            env.set_state(oracle_state_to_engine(cfg, eng.envs))
+    assert diverged <= 1
+    env.close()
