@@ -197,6 +197,8 @@ def run_b200(args):
                  trunc=torch.empty((1, n), dtype=torch.uint8, device=dev)) for _ in range(N_BATCHES)]
     for e in envs:
         e.reset()
+        if args.prewarm > 0:
+            e.rollout_random(args.prewarm)  # K fused steps in one launch: steady-state mix of episode ages
     L = envs[0]._L
     stream = torch.cuda.current_stream(dev)
     # the env batches are independent: each one is stepped on its own stream, forked from / joined into the
@@ -293,12 +295,71 @@ def run_b200(args):
     h2d = n * 2 * 4
     d2h = n * (D * 8 + 8 + 1 + 1)
 
+    # ---- per-kernel durations, live (CUDA events on the launching stream; SG_TIMING handle) -------------
+    kt = None
+    if rank == 0:
+        import ctypes
+        os.environ["SG_TIMING"] = "1"
+        tenv = sg.make(ENV_ID, n, device=dev, seed=4242, copy=False, **ENV_KW)
+        del os.environ["SG_TIMING"]
+        tenv.reset()
+        tenv.rollout_random(max(args.prewarm, 64))
+        ta = actions[0][0]
+        flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > L2: cold inputs for every step
+        buf = (ctypes.c_double * 6)()
+        for k in range(60):
+            if k == 10:
+                L.sg_debug_kernel_times(tenv._h, buf, 1)
+            flush.fill_(k & 255)
+            tenv.step_many(ta)
+        L.sg_debug_kernel_times(tenv._h, buf, 1)
+        kt = {"hot_us": buf[0] * 1e3, "cont_us": buf[1] * 1e3, "tail_us": buf[2] * 1e3,
+              "cont_frac": buf[3] / n, "event_frac": buf[4] / n, "post_frac": buf[5] / n,
+              "how": "50 steps of one 262144-env handle, L2 flushed before every step, CUDA events around each kernel"}
+        tenv.close()
+        del flush
+
+    # ---- end to end with float32 observations (the dtype observation_space declares, spaceship_env.py:110) ----
+    e2e32 = None
+    if not args.no_f32:
+        envs32 = [sg.make(ENV_ID, n, device=dev, seed=2000 + b, first_env_index=rank * n, copy=False,
+                          obs_dtype="float32", **ENV_KW) for b in range(N_BATCHES)]
+        for e in envs32:
+            e.reset()
+        for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(e2e_steps):
+                b = k % N_BATCHES
+                if k >= N_BATCHES:
+                    obs, rew, done, info = envs32[b].step_wait()
+                    checksum += float(rew[0]) + float(obs[-1, 0])
+                envs32[b].step_async(host_acts[(k // N_BATCHES) % ACTION_SETS])
+            for b in range(N_BATCHES):
+                obs, rew, done, info = envs32[b].step_wait()
+                checksum += float(rew[0])
+            barrier()
+            dt32 = time.perf_counter() - t0
+        t32 = torch.tensor([dt32], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+        e2e32 = {"value": total * e2e_steps / float(t32.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": n * (D * 4 + 8 + 1 + 1), "steps": e2e_steps}
+        for e in envs32:
+            e.close()
+
     stats = envs[0].stats(allreduce=world > 1)  # the engine's only collective: episode statistics
 
     if rank == 0:
         hbm_peak, peak_src = read_peaks()
-        launch_s = ms * 1e-3 / args.steps  # the timed region is exactly `steps` sg_step calls (3 kernels x sub-batches each)
+        launch_s = ms * 1e-3 / args.steps  # the timed region is exactly `steps` sg_step calls (3 kernels each)
         achieved_gbs = ALGO_BYTES_PER_STEP * n / launch_s / 1e9
+        # dominant kernel = hot_kernel: it finishes (1 - cont - event) of the env steps of a launch by itself;
+        # only those are counted as its algorithmic work, over its own live-measured duration
+        hot_units = n * (1.0 - kt["cont_frac"] - kt["event_frac"])
+        hot_s = kt["hot_us"] * 1e-6
+        hot_gbs = ALGO_BYTES_PER_STEP * hot_units / hot_s / 1e9
+        hot_tf = ALGO_FLOPS_PER_STEP * hot_units / hot_s / 1e12
         tf = C_double()
         rc = L.sg_measure_fp64_peak(local, 300.0, tf.ref)
         fp64_peak = tf.value if rc == 0 else None
@@ -320,16 +381,25 @@ def run_b200(args):
                        "l2": f"inputs larger than L2: {N_BATCHES} env batches stepped round-robin "
                              f"({N_BATCHES * n * (ALGO_BYTES_PER_STEP + 60) / 1e6:.0f} MB working set)",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "sg::hot_kernel+cont_kernel+tail_kernel<Goal,3P,velocity,f64> (one env step)", "algo_bytes_per_env_step": ALGO_BYTES_PER_STEP,
-                         "launch_ms": launch_s * 1e3},
-            "roofline_fp64": {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                              "frac": (fp64_ach / fp64_peak) if fp64_peak else None,
-                              "algo_flops_per_env_step": ALGO_FLOPS_PER_STEP,
+            "roofline": {"bound": "hbm", "achieved": hot_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": hot_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "sg::hot_kernel<Goal,3P,velocity,f64>", "algo_bytes_per_env_step": ALGO_BYTES_PER_STEP,
+                         "units_per_launch": hot_units, "launch_ms": kt["hot_us"] * 1e-3,
+                         "note": "dominant kernel, duration from CUDA events on its stream with L2 flushed per step; "
+                                 "units = env steps it completes alone"},
+            "roofline_fp64": {"bound": "fp64", "achieved": hot_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": (hot_tf / fp64_peak) if fp64_peak else None,
+                              "algo_flops_per_env_step": ALGO_FLOPS_PER_STEP, "kernel": "sg::hot_kernel",
                               "peak_source": "sg_measure_fp64_peak (DFMA chains, this run)"},
+            "roofline_whole_step": {"hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                            "frac": achieved_gbs / hbm_peak},
+                                    "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                                             "frac": (fp64_ach / fp64_peak) if fp64_peak else None},
+                                    "note": "all kernels of a step (hot+continuation+tail), from `value`"},
+            "kernel_times": kt,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "BatchedSpaceEnv.step_async(numpy)/step_wait() -> sg_step_host_async/sg_host_wait, 4 env batches in flight"},
+            "e2e_f32obs": e2e32,
             "gpu_launches": launches * world,
             "clocks": clocks,
             "episode_stats": stats,
@@ -363,6 +433,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prewarm", type=int, default=128, help="untimed env steps per batch (one fused-kernel launch) that bring the envs to their steady-state mix of episode ages before warm-up")
+    ap.add_argument("--no-f32", action="store_true", help="skip the float32-observation end-to-end leg")
     ap.add_argument("--env-id", default=None, help="benchmark another registered id (default: the BASELINE workload)")
     ap.add_argument("--kwargs", default="{}", help="JSON dict of reference-style kwargs for --env-id")
     args = ap.parse_args()

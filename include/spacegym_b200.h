@@ -165,9 +165,11 @@ int sg_stats_reset(sg_env* env, void* stream);
 uint64_t sg_step_count(const sg_env* env);           /* env steps taken per env (drives the action RNG) */
 int sg_set_step_count(sg_env* env, uint64_t steps);
 int64_t sg_kernel_launches(const sg_env* env);       /* kernels launched by this handle */
-/* Debugging aid, active when the handle was created with SG_TIMING=1 in the environment (sg_step then
- * synchronises after every step): mean milliseconds of the {hot, continuation, tail} kernels per env step. */
-int sg_debug_kernel_times(sg_env* env, double out[3], int reset);
+/* Measurement aid, active when the handle was created with SG_TIMING=1 in the environment (sg_step then
+ * synchronises inside every step): out[0..2] = mean milliseconds of the {hot, continuation, tail} kernels per
+ * env step (CUDA events on the launching stream), out[3..5] = mean entries of the {continuation, event, post}
+ * queues per step. */
+int sg_debug_kernel_times(sg_env* env, double out[6], int reset);
 
 /* ---- measurement helpers ----------------------------------------------------- */
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), measured

@@ -982,6 +982,7 @@ struct sg_env {
     int timing;                 // SG_TIMING=1: CUDA events around every kernel of the split path
     cudaEvent_t tev[5];
     double t_acc[4];
+    double q_acc[3];            // mean entries of the continuation / event / post queues
     long long t_n;
     struct GraphEntry {
         const void* key[5];
@@ -1350,6 +1351,7 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
         h->timing = env_tm ? atoi(env_tm) : 0;
         h->t_n = 0;
         for (int k = 0; k < 4; ++k) h->t_acc[k] = 0;
+        for (int k = 0; k < 3; ++k) h->q_acc[k] = 0;
         for (int k = 0; k < 5; ++k) {
             h->tev[k] = nullptr;
             if (h->timing && err == cudaSuccess) err = cudaEventCreate(&h->tev[k]);
@@ -1439,12 +1441,14 @@ extern "C" int sg_set_step_count(sg_env* h, uint64_t s) {
 extern "C" int64_t sg_kernel_launches(const sg_env* h) { return h ? h->launches : 0; }
 
 // debugging aid (SG_TIMING=1): mean milliseconds of {hot, continuation, tail} per env step so far
-extern "C" int sg_debug_kernel_times(sg_env* h, double out[3], int reset) {
+extern "C" int sg_debug_kernel_times(sg_env* h, double out[6], int reset) {
     if (!h || !out) return SG_ERR_INVALID;
     for (int k = 0; k < 3; ++k) out[k] = h->t_n ? h->t_acc[k] / (double)h->t_n : 0.0;
+    for (int k = 0; k < 3; ++k) out[3 + k] = h->t_n ? h->q_acc[k] / (double)h->t_n : 0.0;
     if (reset) {
         h->t_n = 0;
         for (int k = 0; k < 4; ++k) h->t_acc[k] = 0;
+        for (int k = 0; k < 3; ++k) h->q_acc[k] = 0;
     }
     return SG_OK;
 }
@@ -1509,16 +1513,25 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
             cont_kernel<TR, OT><<<sms, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr, 1);
         else
             cont_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr, 0);
-        if (h->timing) cudaEventRecord(h->tev[2], small);
+        if (h->timing) {
+            cudaEventRecord(h->tev[2], small);
+            uint32_t qc[3] = {0, 0, 0};
+            cudaMemcpyAsync(qc, sb.dev.q_counts, sizeof(qc), cudaMemcpyDeviceToHost, small);
+            cudaStreamSynchronize(small);
+            for (int k = 0; k < 3; ++k) hm->q_acc[k] += qc[k];
+            cudaEventRecord(h->tev[4], small);
+        }
         tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
         if (h->timing) {  // debugging aid: synchronous, never on in benchmarks
             cudaEventRecord(h->tev[3], small);
             cudaEventSynchronize(h->tev[3]);
             float ms = 0;
-            for (int k = 0; k < 3; ++k) {
-                cudaEventElapsedTime(&ms, h->tev[k], h->tev[k + 1]);
-                hm->t_acc[k] += ms;
-            }
+            cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]);
+            hm->t_acc[0] += ms;
+            cudaEventElapsedTime(&ms, h->tev[1], h->tev[2]);
+            hm->t_acc[1] += ms;
+            cudaEventElapsedTime(&ms, h->tev[4], h->tev[3]);
+            hm->t_acc[2] += ms;
             hm->t_n += 1;
         }
         if (a.hi_stream) {
