@@ -188,7 +188,9 @@ struct Rng {
         have_u = have_n = false;
     }
     __device__ __forceinline__ void fresh_block() { have_u = have_n = false; }
-    __device__ double uniform() {
+    // __noinline__: resets draw ~30 numbers; one copy of the Philox rounds instead of 30 keeps the cold
+    // kernels' code (and their instruction-cache misses) small
+    __device__ __noinline__ double uniform() {
         if (have_u) {
             have_u = false;
             return ubuf;
@@ -202,7 +204,7 @@ struct Rng {
         have_u = true;
         return (double)(a >> 11) * (1.0 / 9007199254740992.0);
     }
-    __device__ double normal() {  // Box-Muller
+    __device__ __noinline__ double normal() {  // Box-Muller
         if (have_n) {
             have_n = false;
             return nbuf;
@@ -628,6 +630,9 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     event_values(c, e, x, y, om, g, pd);
 }
 
+// out-of-line sincos for the cold paths (reset placement, terminal states): one copy of the range reduction
+__device__ __noinline__ void sincos_cold(double a, double* s, double* c) { sincos(a, s, c); }
+
 struct SinCos6 {
     double s[6], c[6];
 };
@@ -1047,7 +1052,7 @@ __device__ inline void store_tiles(const DevCfg& c, long long i, const Tiles& t,
 }
 
 // HexagonalTiling._tile_center_pos (hexagonal_tiling.py:136-158)
-__device__ inline void tile_center(const DevCfg& c, const Tiles& t, int tile, double& ox, double& oy) {
+__device__ __noinline__ void tile_center(const DevCfg& c, const Tiles& t, int tile, double& ox, double& oy) {
     int row = tile / c.cols, col = tile % c.cols;
     double zero_x = -c.ws / 2 + c.hex_width / 2;
     double zero_y = c.ws / 2 - c.hex_height / 2;
@@ -1096,7 +1101,7 @@ __device__ inline void choice_no_replace(Rng& rng, int n, int k, int (&out)[KMAX
 }
 
 // HexagonalTiling.find_new_goal (hexagonal_tiling.py:95-134)
-__device__ inline void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double& gx, double& gy, uint32_t& status) {
+__device__ __noinline__ void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double& gx, double& gy, uint32_t& status) {
     if (t.goal_tile != 63u) {
         if (t.n_free < 64u) {
             t.set(t.n_free, t.ship_tile);
@@ -1136,7 +1141,7 @@ __device__ inline void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double
     double ang = kTwoPi * rng.uniform();
     double rr = sqrt(rng.uniform() * (R * R));
     double sn, cs;
-    sincos(ang, &sn, &cs);
+    sincos_cold(ang, &sn, &cs);
     gx = cx + rr * cs;
     gy = cy + rr * sn;
 }
@@ -1208,7 +1213,7 @@ __device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, 
             double rr = sqrt(rng.uniform() * (R * R));
             double cx, cy, sn, cs;
             tile_center(c, t, tiles[j], cx, cy);
-            sincos(ang[j], &sn, &cs);
+            sincos_cold(ang[j], &sn, &cs);
             double ox = cx + rr * cs, oy = cy + rr * sn;
             if (j == 0) {
                 out[0] = ox;
@@ -1230,7 +1235,7 @@ __device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, 
         double pang = kTwoPi * rng.uniform();
         double dist = c.kep_lo + (c.kep_hi - c.kep_lo) * rng.uniform();
         double sn, cs;
-        sincos(pang, &sn, &cs);
+        sincos_cold(pang, &sn, &cs);
         out[0] = cs * dist;
         out[1] = sn * dist;
         out[2] = kTwoPi * rng.uniform();

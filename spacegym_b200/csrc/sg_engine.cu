@@ -803,6 +803,8 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
     double st[4] = {0, 0, 0, 0};
     for (uint32_t base = blockIdx.x * kTailBlock; base < total; base += gridDim.x * kTailBlock) {
         const uint32_t j = base + threadIdx.x;
+        long long post_i = 0;
+        bool post_reached = false, post_done = false, do_post = false;
         if (j < n_event) {
             const long long i = c.q_event[j];
             EnvRegs<TR> e;
@@ -831,7 +833,7 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
             double gd[TR::NEV], pd[TR::NP];
             event_values(c, e, e.x, e.y, e.om, gd, pd);
             double sn, cs;
-            sincos(e.th, &sn, &cs);
+            sincos_cold(e.th, &sn, &cs);
             OT row[TR::D];
             const bool want_row = obs && !c.auto_reset;  // with auto-reset the reset observation replaces it
             bool reached, done;
@@ -845,11 +847,20 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
                 for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
             }
             if (status) c.status[i] |= status;
-            post_env<TR, OT>(c, i, reached, done, obs);
+            post_i = i;
+            post_reached = reached;
+            post_done = done;
+            do_post = true;
         } else if (j < total) {
             const uint32_t w = c.q_post[j - n_event];
-            post_env<TR, OT>(c, (long long)(w & kPostIndex), (w & kPostReached) != 0, (w & kPostDone) != 0, obs);
+            post_i = (long long)(w & kPostIndex);
+            post_reached = (w & kPostReached) != 0;
+            post_done = (w & kPostDone) != 0;
+            do_post = true;
         }
+        // one call site for both kinds of entries: the reset code exists once (this kernel runs each
+        // instruction once per warp, so its time is largely instruction-fetch latency)
+        if (do_post) post_env<TR, OT>(c, post_i, post_reached, post_done, obs);
     }
     block_stats_flush<kTailBlock>(c, st);
     // the last block to finish empties the queues for the next step
