@@ -8,8 +8,9 @@ Workload (BASELINE.json configs[2], the config the north-star target is quoted o
 GoalContinuous3P-v0, 262144 envs per step and per GPU, auto-reset with hexagonal-tiling
 placement, TimeLimit 500, uniform random float32 actions.  A "step" is one env.step() of one
 batch of 262144 envs (one `sg_step` launch, K=1: actions read from HBM, observation, reward
-and done written to HBM).  Four independent env batches are stepped round-robin so that the
-working set (4 x 86 MB state+outputs) exceeds the 126 MB L2 between revisits.
+and done written to HBM).  Eight independent env batches (each on its own stream) are stepped
+round-robin, so that the working set (8 x 100 MB state+outputs) exceeds the 126 MB L2 between revisits
+and the latency-bound continuation / tail kernels of one batch overlap the hot kernel of another.
 
 Prints ONE JSON line (rank 0).  `value` = device-timed (CUDA events, max over ranks) whole-job
 env-steps/s with inputs resident in HBM; `e2e` = the same through BatchedSpaceEnv.step with
@@ -35,7 +36,7 @@ sys.path.insert(0, ROOT)
 ENV_ID = "GoalContinuous3P-v0"
 ENV_KW = {}
 ENVS_PER_STEP = 262144
-N_BATCHES = 4
+N_BATCHES = 8
 ACTION_SETS = 4
 # SURVEY.md §8d contract figures for GoalContinuous3P-v0 (per env step, K=1, f64 observation)
 ALGO_BYTES_PER_STEP = 329.0
@@ -261,7 +262,7 @@ def run_b200(args):
     value = total * args.steps / (ms * 1e-3)
 
     # ---- end to end: public API with host buffers (pinned), copies inside the timed region ----
-    # gym.vector step_async / step_wait over the same four env batches: every step uploads its actions
+    # gym.vector step_async / step_wait over the same env batches: every step uploads its actions
     # from host memory and downloads observation, reward, done and truncated into host memory.
     e2e_steps = max(N_BATCHES, min(args.steps, 200) // N_BATCHES * N_BATCHES)
     host_acts = [np.random.RandomState(7 + rank + i).uniform(-1, 1, size=(n, 2)).astype(np.float32)
@@ -398,7 +399,7 @@ def run_b200(args):
                                     "note": "all kernels of a step (hot+continuation+tail), from `value`"},
             "kernel_times": kt,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchedSpaceEnv.step_async(numpy)/step_wait() -> sg_step_host_async/sg_host_wait, 4 env batches in flight"},
+                    "steps": e2e_steps, "api": "BatchedSpaceEnv.step_async(numpy)/step_wait() -> sg_step_host_async/sg_host_wait, all env batches in flight"},
             "e2e_f32obs": e2e32,
             "gpu_launches": launches * world,
             "clocks": clocks,
@@ -434,11 +435,14 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm", type=int, default=128, help="untimed env steps per batch (one fused-kernel launch) that bring the envs to their steady-state mix of episode ages before warm-up")
+    ap.add_argument("--batches", type=int, default=None, help="independent env batches in flight (default 8)")
     ap.add_argument("--no-f32", action="store_true", help="skip the float32-observation end-to-end leg")
     ap.add_argument("--env-id", default=None, help="benchmark another registered id (default: the BASELINE workload)")
     ap.add_argument("--kwargs", default="{}", help="JSON dict of reference-style kwargs for --env-id")
     args = ap.parse_args()
-    global ENV_ID, ENV_KW
+    global ENV_ID, ENV_KW, N_BATCHES
+    if args.batches:
+        N_BATCHES = args.batches
     if args.env_id:
         ENV_ID = args.env_id
     ENV_KW = json.loads(args.kwargs)

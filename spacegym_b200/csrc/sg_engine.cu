@@ -115,6 +115,26 @@ __device__ __forceinline__ void flush_obs(const OT* sobs, OT* obs, long long blo
     for (long long j = nvec * V + threadIdx.x; j < total; j += kBlock) dst[j] = sobs[j];
 }
 
+// Warp-cooperative copy of the warp's own 32 staged observation rows (contiguous in global memory):
+// 128-bit coalesced stores without a block-wide barrier.
+template <typename OT, int D>
+__device__ __forceinline__ void flush_obs_warp(const OT* sobs, OT* obs, long long block_first, long long n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long first = block_first + 32 * warp;
+    long long rows = n - first;
+    if (rows <= 0) return;
+    if (rows > 32) rows = 32;
+    const long long total = rows * D;             // elements
+    const OT* src = sobs + 32 * warp * D;          // 16-byte aligned: 32 * D * sizeof(OT) is a multiple of 16
+    OT* dst = obs + first * D;
+    constexpr int V = 16 / sizeof(OT);
+    const long long nvec = total / V;
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (long long j = lane; j < nvec; j += 32) d4[j] = s4[j];
+    for (long long j = nvec * V + lane; j < total; j += 32) dst[j] = src[j];
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -295,6 +315,16 @@ __device__ __forceinline__ void queue_push3(uint32_t* c0, bool n0, uint32_t* c1,
     s0 = __shfl_sync(0xffffffffu, b0, 0) + (uint32_t)__popc(m0 & below);
     s1 = __shfl_sync(0xffffffffu, b1, 0) + (uint32_t)__popc(m1 & below);
     s2 = __shfl_sync(0xffffffffu, b2, 0) + (uint32_t)__popc(m2 & below);
+}
+
+// episode statistics: warp shuffle, then one atomic per warp and non-zero counter (no block barrier)
+__device__ __forceinline__ void warp_stats_flush(const DevCfg& c, double (&st)[4]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double v = warp_sum(st[k]);
+        if (lane == k && v != 0) atomicAdd(&c.stats[k], v);
+    }
 }
 
 template <int BLOCK>
@@ -483,7 +513,7 @@ __device__ __forceinline__ void save_event(const DevCfg& c, uint32_t slot, long 
     p[22 * cap] = lx; p[23 * cap] = ly; p[24 * cap] = (double)active;
 }
 
-enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2 };
+enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2, KIND_FINISH = 3 };
 
 #ifndef SG_HOT_MINB
 #define SG_HOT_MINB 4
@@ -493,11 +523,90 @@ enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2 };
 #endif
 // One chunk of kBlock envs through the common path.  `publish` = true (fused persistent kernel): a
 // continuation entry becomes visible to the in-kernel consumers by the release of its index word.
-template <class TR, typename OT>
+// ---- staged inputs of the persistent hot kernel ---------------------------------------------------------
+// Every thread copies the fields of ITS OWN env of the next chunk into shared memory with cp.async while it
+// integrates the current chunk, so the DRAM latency of the state load (19 % of the warp's life in the
+// non-staged kernel) is off the critical path.  No block barrier is needed: a thread only reads what it copied.
+template <class TR>
+struct Stage {
+    static constexpr int NF = (TR::TASK == TASK_GOAL ? 6 + 2 * TR::NP + 2 : 6 + 2) + 2;  // + ep_return + action
+    double f[NF][kBlock];
+    uint32_t elapsed[kBlock];
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class TR>
+__device__ __forceinline__ void stage_prefetch(const DevCfg& c, const float* __restrict__ actions, long long i,
+                                               Stage<TR>& s) {
+    const int t = threadIdx.x;
+    if (i < c.n) {
+        const long long n = c.stride;
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) cp_async8(&s.f[k++][t], c.ship + r * n + i);
+        if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+            for (int r = 0; r < 2 * TR::NP; ++r) cp_async8(&s.f[k++][t], c.planets + r * n + i);
+            cp_async8(&s.f[k++][t], c.goal + i);
+            cp_async8(&s.f[k++][t], c.goal + n + i);
+        } else {
+            cp_async8(&s.f[k++][t], c.orbit + i);
+            cp_async8(&s.f[k++][t], c.orbit + n + i);
+        }
+        cp_async8(&s.f[k++][t], c.ep_return + i);
+        if (actions) cp_async8(&s.f[k++][t], reinterpret_cast<const float2*>(actions) + i);
+        cp_async4(&s.elapsed[t], c.elapsed + i);
+    }
+}
+
+template <class TR>
+__device__ __forceinline__ void stage_load(const DevCfg& c, const Stage<TR>& s, bool have_actions, EnvRegs<TR>& e,
+                                           float& r0, float& r1, uint32_t& elapsed0, double& ep_ret0) {
+    const int t = threadIdx.x;
+    int k = 0;
+    e.x = s.f[k++][t]; e.y = s.f[k++][t]; e.th = s.f[k++][t]; e.vx = s.f[k++][t]; e.vy = s.f[k++][t]; e.om = s.f[k++][t];
+    if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+        for (int p = 0; p < TR::NP; ++p) {
+            e.px[p] = s.f[k++][t];
+            e.py[p] = s.f[k++][t];
+        }
+        e.gx = s.f[k++][t];
+        e.gy = s.f[k++][t];
+        e.ecc = e.ang = 0.0;
+    } else {
+        e.px[0] = e.py[0] = 0.0;
+        e.gx = e.gy = 0.0;
+        e.ecc = s.f[k++][t];
+        e.ang = s.f[k++][t];
+    }
+    ep_ret0 = s.f[k++][t];
+    r0 = r1 = 0.0f;
+    if (have_actions) {
+        const float2 a = *reinterpret_cast<const float2*>(&s.f[k][t]);
+        r0 = a.x;
+        r1 = a.y;
+    }
+    elapsed0 = s.elapsed[t];
+}
+
+template <class TR, typename OT, bool STAGED = false>
 __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restrict__ actions, unsigned long long step0,
                                           OT* __restrict__ obs, double* __restrict__ reward,
                                           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
-                                          long long block_first, OT* sobs, double (&st)[4], bool publish) {
+                                          long long block_first, OT* sobs, double (&st)[4], bool publish,
+                                          const Stage<TR>* stage = nullptr) {
     constexpr int D = TR::D;
     const long long i = block_first + threadIdx.x;
     const bool valid = i < c.n;
@@ -505,15 +614,28 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     bool need_post = false, reached = false, done = false, rejected = false;
     Integ<TR> S;
     double Ax[7], Ay[7], h = 0, lx = 0, ly = 0;
+    double fx = 0, fy = 0, fth = 0, fvx = 0, fvy = 0, fom = 0, fcn = 1, fsn = 0, fpd[TR::NP], fipd[TR::NP];
     uint32_t active = 0;
 
     EnvRegs<TR> e;
     Act act;
-    if (valid) {
+    uint32_t elapsed0 = 0;
+    double ep_ret0 = 0.0;
+    if (STAGED) {
+        float r0 = 0.0f, r1 = 0.0f;
+        if (valid) stage_load<TR>(c, *stage, actions != nullptr, e, r0, r1, elapsed0, ep_ret0);
+        __syncthreads();  // the stage buffer is reused as the observation staging area of this chunk
+        if (valid) {
+            if (!actions) random_action(c.seed, (unsigned long long)(c.first_env + i), step0, TR::DISC != 0, r0, r1);
+            act = translate_action<TR>(c, r0, r1);
+        }
+    } else if (valid) {
         load_env<TR>(c, i, e);
         act = fetch_action<TR>(c, actions, i, step0);
-        const uint32_t elapsed0 = c.elapsed[i];  // fetched with the state: not on the critical path of the epilogue
-        const double ep_ret0 = c.ep_return[i];
+        elapsed0 = c.elapsed[i];  // fetched with the state: not on the critical path of the epilogue
+        ep_ret0 = c.ep_return[i];
+    }
+    if (valid) {
         lx = e.x;
         ly = e.y;  // env.last_xy (spaceship_env.py:74)
         double g[TR::NEV], pd[TR::NP];
@@ -538,19 +660,39 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
                 S.x = xn; S.y = yn; S.th = thn; S.vx = vxn; S.vy = vyn; S.om = omn;
                 S.cth = cn; S.sth = sn; S.Ax = Ax[6]; S.Ay = Ay[6]; S.t = t_new;
             } else {
-                uint32_t status = 0;
-                commit_state<TR>(e, xn, yn, thn, vxn, vyn, omn, status);
-                finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, false, obs ? sobs + threadIdx.x * D : nullptr, cn, sn,
-                                   elapsed0, ep_ret0, reward, done_out, trunc_out, st, reached, done);
-                need_post = reached || (done && c.auto_reset);
-                if (status) c.status[i] |= status;
+                kind = KIND_FINISH;
+                fx = xn; fy = yn; fth = thn; fvx = vxn; fvy = vyn; fom = omn; fcn = cn; fsn = sn;
+#pragma unroll
+                for (int p = 0; p < TR::NP; ++p) {
+                    fpd[p] = pd[p];
+                    fipd[p] = ipd[p];
+                }
             }
         }
     }
-    // queue appends at warp-converged points
-    uint32_t s_cont, s_event, s_post;
-    queue_push3(&c.q_counts[0], kind == KIND_CONT, &c.q_counts[1], kind == KIND_EVENT, &c.q_counts[2], need_post, s_cont,
-                s_event, s_post);
+    // queue appends at warp-converged points.  The continuation / event atomics are issued BEFORE the
+    // epilogue of the finished lanes, whose arithmetic then covers the L2 round trip of the atomics.
+    const unsigned m_cont = __ballot_sync(0xffffffffu, kind == KIND_CONT);
+    const unsigned m_event = __ballot_sync(0xffffffffu, kind == KIND_EVENT);
+    const int lane = threadIdx.x & 31;
+    uint32_t b_cont = 0, b_event = 0;
+    if (lane == 0) {
+        if (m_cont) b_cont = atomicAdd(&c.q_counts[0], (uint32_t)__popc(m_cont));
+        if (m_event) b_event = atomicAdd(&c.q_counts[1], (uint32_t)__popc(m_event));
+    }
+    if (kind == KIND_FINISH) {
+        uint32_t status = 0;
+        commit_state<TR>(e, fx, fy, fth, fvx, fvy, fom, status);
+        finish_env<TR, OT>(c, i, e, act, lx, ly, fpd, fipd, false, obs ? sobs + threadIdx.x * D : nullptr, fcn, fsn,
+                           elapsed0, ep_ret0, reward, done_out, trunc_out, st, reached, done);
+        need_post = reached || (done && c.auto_reset);
+        if (status) c.status[i] |= status;
+        kind = KIND_DONE;
+    }
+    const unsigned below = (1u << lane) - 1u;
+    const uint32_t s_cont = __shfl_sync(0xffffffffu, b_cont, 0) + (uint32_t)__popc(m_cont & below);
+    const uint32_t s_event = __shfl_sync(0xffffffffu, b_event, 0) + (uint32_t)__popc(m_event & below);
+    const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
     if (kind == KIND_CONT) {
         save_cont<TR>(c, c.q_cont, c.scr_cont, s_cont, i, S, lx, ly, rejected, !publish);
         save_cont_scene<TR>(c, c.scr_cont, s_cont, e, act);
@@ -558,9 +700,14 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     }
     if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
     if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
-    if (obs) {
-        __syncthreads();
-        flush_obs<OT, D>(sobs, obs, block_first, c.n);  // rows of queued envs are rewritten by the later kernels
+    if (obs) {  // rows of queued envs are rewritten by the later kernels
+        if (STAGED) {
+            __syncthreads();
+            flush_obs<OT, D>(sobs, obs, block_first, c.n);
+        } else {
+            __syncwarp();
+            flush_obs_warp<OT, D>(sobs, obs, block_first, c.n);
+        }
     }
 }
 
@@ -572,7 +719,7 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
     __shared__ __align__(16) OT sobs[kBlock * TR::D];
     double st[4] = {0, 0, 0, 0};
     hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)blockIdx.x * kBlock, sobs, st, false);
-    block_stats_flush<kBlock>(c, st);
+    warp_stats_flush(c, st);
 }
 
 template <class TR>
@@ -587,6 +734,33 @@ __device__ __forceinline__ void load_cont(const DevCfg& c, const double* scr, ui
     rejected = p[14 * cap] != 0.0;
     S.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
     S.fs = act.fs;
+}
+
+// Persistent form of the hot kernel (default): gridDim = resident CTAs, each walks chunks blockIdx.x, + gridDim.x,
+// ... with the next chunk's inputs in flight (cp.async, two stages) while the current one is integrated.
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
+hot_staged_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+                  uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out, uint32_t n_chunks) {
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
+    __shared__ __align__(16) Stage<TR> stages[2];
+    static_assert(sizeof(Stage<TR>) >= sizeof(OT) * kBlock * TR::D, "a consumed stage doubles as the obs staging area");
+    double st[4] = {0, 0, 0, 0};
+    uint32_t chunk = blockIdx.x;
+    int cur = 0;
+    if (chunk < n_chunks) stage_prefetch<TR>(c, actions, (long long)chunk * kBlock + threadIdx.x, stages[0]);
+    cp_async_commit();
+    for (; chunk < n_chunks; chunk += gridDim.x, cur ^= 1) {
+        const uint32_t next = chunk + gridDim.x;
+        if (next < n_chunks) stage_prefetch<TR>(c, actions, (long long)next * kBlock + threadIdx.x, stages[cur ^ 1]);
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the group just committed has landed: this chunk's inputs
+        hot_chunk<TR, OT, true>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)chunk * kBlock,
+                                reinterpret_cast<OT*>(&stages[cur]), st, false, &stages[cur]);
+        __syncthreads();  // the rows staged in stages[cur] are flushed before the next prefetch overwrites them
+    }
+    cp_async_wait<0>();
+    block_stats_flush<kBlock>(c, st);
 }
 
 // One more Runge-Kutta attempt for continuation entry j of the first queue (valid = the entry exists).
@@ -989,7 +1163,7 @@ struct sg_env {
     // their blocks are scheduled ahead of the pending hot-kernel blocks of other handles' steps
     cudaStream_t hi_stream;
     cudaEvent_t ev_hot, ev_tail;
-    int use_priority, use_fused, use_cont1;
+    int use_priority, use_fused, use_cont1, use_staged;
     int timing;                 // SG_TIMING=1: CUDA events around every kernel of the split path
     cudaEvent_t tev[5];
     double t_acc[4];
@@ -1356,6 +1530,8 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
         const char* env_fused = getenv("SG_FUSED");
         h->use_fused = env_fused ? atoi(env_fused) : 0;
+        const char* env_sg = getenv("SG_STAGED");
+        h->use_staged = env_sg ? atoi(env_sg) : 0;  // measured neutral (profiles/r1_notes.md)
         const char* env_c1 = getenv("SG_CONT1");
         h->use_cont1 = env_c1 ? atoi(env_c1) : 0;
         const char* env_tm = getenv("SG_TIMING");
@@ -1507,6 +1683,9 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         if (h->use_fused) {
             int fused_blocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
             fused_kernel<TR, OT><<<fused_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
+        } else if (h->use_staged) {
+            int pblocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
+            hot_staged_kernel<TR, OT><<<pblocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
         } else {
             hot_kernel<TR, OT><<<hot_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
         }
