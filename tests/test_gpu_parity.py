@@ -282,3 +282,80 @@ def test_alternative_step_plans_match_oracle(oracle, plan, monkeypatch):
             env.set_state(oracle_state_to_engine(cfg, eng.envs))
     assert diverged <= 1
     env.close()
+
+
+def _spot_check_against_oracle(oracle, case, env, cfg, n_check, rng):
+    """Step the whole (large) env once and compare a random subset of transitions with the oracle."""
+    n = env.num_envs
+    st = env.get_state()
+    idx = np.sort(rng.choice(n, size=n_check, replace=False))
+    act = torch.rand((n, 2), device=env.device, generator=torch.Generator(device=env.device).manual_seed(5)) * 2 - 1
+    act = act.float().contiguous()
+    ship0 = st["ship"][idx].cpu().numpy()
+    if cfg.task == 0:
+        planets0 = st["planets"][idx].cpu().numpy()
+        goal0 = st["goal"][idx].cpu().numpy()
+        orbit0 = np.zeros((n_check, 3))
+    else:
+        planets0 = np.zeros((n_check, 2, 2))
+        goal0 = np.zeros((n_check, 2))
+        orb = st["orbit"][idx].cpu().numpy()
+        orbit0 = np.stack([orb[:, 1], orb[:, 0], np.full(n_check, cfg.ref_orbit_a)], axis=1)  # (angle, ecc, a)
+    elapsed0 = st["elapsed"][idx].cpu().numpy()
+    obs, rew, done, info = env.step(act)
+    a_np = act[idx].cpu().numpy()
+    obs_np, rew_np, done_np = obs[idx].cpu().numpy(), rew[idx].cpu().numpy(), done[idx].cpu().numpy()
+    bad = 0
+    for k in range(n_check):
+        r = oracle.step_transition(cfg, ship0[k], planets0[k], goal0[k], orbit0[k], a_np[k])
+        dn = r["done"] or (elapsed0[k] + 1 >= cfg.max_episode_steps)
+        ok = (dn == bool(done_np[k])) and close(rew_np[k], r["reward"]).all()
+        if not dn:  # a done env returns its reset observation (other RNG draws than this one-shot oracle call)
+            ok = ok and close(obs_np[k], r["obs"]).all()
+        bad += 0 if ok else 1
+    return bad
+
+
+def test_config4_kepler_hard_randomize_accel_1m(oracle):
+    """BASELINE config 4: KeplerEllipseHard-v0, randomize=True, angular-acceleration steering, 1M envs."""
+    n = 1 << 20
+    env = sg.make("KeplerEllipseHard-v0", n, seed=11, randomize=True, ship_steering=0)
+    cfg = oracle.config_from_id("KeplerEllipseHard-v0", randomize=1, ship_steering=0)
+    obs = env.reset()
+    assert obs.shape == (n, 10) and torch.isfinite(obs).all()
+    env.rollout_random(40)
+    assert _spot_check_against_oracle(oracle, "kepler", env, cfg, 1500, np.random.RandomState(0)) == 0
+    obs, rew, done, _ = env.step_many(K=20)
+    st = env.get_state()
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and int(st["status"].abs().sum()) == 0
+    assert (rew > 0).all() and (rew <= 1).all()  # C / (penalties + C)
+    orb = st["orbit"]
+    assert (orb[:, 0] >= 0).all() and (orb[:, 0] < 0.7).all() and (orb[:, 1] >= 0).all() and (orb[:, 1] < 2 * np.pi).all()
+    r = st["ship"][:, :2].norm(dim=1)
+    assert (r >= 0.2 - 1e-9).all() and (r <= 3.0 + 1e-9).all() and (st["ship"][:, 5].abs() <= 6 + 1e-9).all()
+    s = env.stats()
+    assert s["episodes"] > 0 and abs(s["length_sum"] + float(st["elapsed"].sum()) - 61.0 * n) < 0.5
+    env.close()
+
+
+def test_config5_goal4p_4m_envs_sharded(oracle):
+    """BASELINE config 5 (one shard of it): GoalContinuous4P-v0, 4M envs, as two shards keyed by global index."""
+    n = 1 << 21
+    cfg = oracle.config_from_id("GoalContinuous4P-v0")
+    shards = [sg.make("GoalContinuous4P-v0", n, seed=5, first_env_index=k * n) for k in range(2)]
+    bad = 0
+    for k, env in enumerate(shards):
+        obs = env.reset()
+        assert obs.shape == (n, 17) and torch.isfinite(obs).all()
+        env.rollout_random(30)
+        bad += _spot_check_against_oracle(oracle, "goal", env, cfg, 1000, np.random.RandomState(k))
+        st = env.get_state()
+        assert int(st["status"].abs().sum()) == 0 and (st["ship"][:, :2].abs() <= 1.5).all()
+    assert bad == 0
+    # different global indices -> different streams (no duplicated envs across shards)
+    a, b = shards[0].get_state()["ship"][:1000], shards[1].get_state()["ship"][:1000]
+    assert not torch.equal(a, b)
+    tot = sum(e.stats()["episodes"] for e in shards)
+    assert tot > 0.01 * 31 * 2 * n * 0.5
+    for e in shards:
+        e.close()
