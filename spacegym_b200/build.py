@@ -17,7 +17,8 @@ OUT = os.path.join(HERE, "libspacegym_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-]
+]  # no --split-compile: it halves the build time but the kernels come out 3-5 % slower
+
 
 
 def needs_build():

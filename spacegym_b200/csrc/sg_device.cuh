@@ -310,6 +310,28 @@ template <class TR>
 __device__ __forceinline__ void event_values_from_pd(const DevCfg& c, double x, double y, double om,
                                                      const double (&pd)[TR::NP], double (&g)[TR::NEV]);
 
+// same force, also returning |planet - ship| and its inverse: the event check at the same point reuses them
+template <class TR>
+__device__ __forceinline__ void accel_pd(const DevCfg& c, const EnvRegs<TR>& e, double x, double y, double cth,
+                                         double sth, double fs, double& ax, double& ay, double (&pd)[TR::NP],
+                                         double (&ipd)[TR::NP]) {
+    double fx = -cth * fs, fy = -sth * fs;
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        double dx = e.px[p] - x, dy = e.py[p] - y;
+        const double d2 = dx * dx + dy * dy;
+        const double inv = fast_rsqrt(d2);
+        const double sq = d2 * inv;
+        pd[p] = fma(fma(-sq, sq, d2), 0.5 * inv, sq);  // fast_sqrt(d2) from the same rsqrt
+        ipd[p] = inv;
+        double s = c.gm0 * (inv * inv * inv);
+        fx = fma(dx, s, fx);
+        fy = fma(dy, s, fy);
+    }
+    ax = fx * c.inv_mass;
+    ay = fy * c.inv_mass;
+}
+
 // ---- termination events (dynamic_model.py:183-217) -------------------------------------------------
 // order: planets..., world_max, world_min, angular velocity.  pd = planet-centre distances.
 template <class TR>
@@ -584,7 +606,8 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     S.x = e.x; S.y = e.y; S.th = e.th; S.vx = e.vx; S.vy = e.vy; S.om = e.om;
     S.t = 0.0;
     sincos(S.th, &S.sth, &S.cth);
-    accel(c, e, S.x, S.y, S.cth, S.sth, S.fs, S.Ax, S.Ay);  // f0
+    double ipd0[TR::NP];
+    accel_pd<TR>(c, e, S.x, S.y, S.cth, S.sth, S.fs, S.Ax, S.Ay, pd, ipd0);  // f0 (+ planet distances for g(t0))
     const double x = S.x, y = S.y, th = S.th, vx = S.vx, vy = S.vy, om = S.om, alpha = S.alpha;
     double rx = fast_rcp(kAtol + fabs(x) * kRtol), ry = fast_rcp(kAtol + fabs(y) * kRtol);
     double rth = fast_rcp(kAtol + fabs(th) * kRtol), rvx = fast_rcp(kAtol + fabs(vx) * kRtol);
@@ -627,7 +650,7 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
         else h_abs = fmin(lim, pow(fast_div(0.01, dm), 0.2));
     }
     S.h_abs = h_abs;
-    event_values(c, e, x, y, om, g, pd);
+    event_values_from_pd<TR>(c, x, y, om, pd, g);
 }
 
 // out-of-line sincos for the cold paths (reset placement, terminal states): one copy of the range reduction
@@ -688,7 +711,7 @@ template <class TR>
 __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e, const Integ<TR>& S, double h,
                                            double (&Ax)[7], double (&Ay)[7], double& xn, double& yn, double& thn,
                                            double& vxn, double& vyn, double& omn, double& cn, double& sn,
-                                           double& err2) {
+                                           double& err2, double (&pdn)[TR::NP], double (&ipdn)[TR::NP]) {
     const double x = S.x, y = S.y, vx = S.vx, vy = S.vy;
     const double hh = h * h, ho = h * S.om, ha = hh * S.alpha;
     const bool small = fabs(ho) + fabs(ha) < 0.5;
@@ -726,7 +749,7 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     omn = S.om + h * S.alpha;
     cn = cr[5];
     sn = sr[5];
-    accel(c, e, xn, yn, cn, sn, S.fs, Ax[6], Ay[6]);  // f_new (FSAL)
+    accel_pd<TR>(c, e, xn, yn, cn, sn, S.fs, Ax[6], Ay[6], pdn, ipdn);  // f_new (FSAL) + distances at the end point
     double ex = hh * (eb1 * Ax[0] + eb2 * Ax[1] + eb3 * Ax[2] + eb4 * Ax[3] + eb5 * Ax[4] + eb6 * Ax[5]);
     double ey = hh * (eb1 * Ay[0] + eb2 * Ay[1] + eb3 * Ay[2] + eb4 * Ay[3] + eb5 * Ay[4] + eb6 * Ay[5]);
     double evx = h * (e1 * Ax[0] + e3 * Ax[2] + e4 * Ax[3] + e5 * Ax[4] + e6 * Ax[5] + e7 * Ax[6]);
@@ -801,19 +824,19 @@ __device__ __forceinline__ int rk_loop(const DevCfg& c, const EnvRegs<TR>& e, In
     for (;;) {
         const double min_step = min_step_at(S.t);
         if (S.h_abs < min_step && !rejected) S.h_abs = min_step;
-        double Ax[7], Ay[7], xn, yn, thn, vxn, vyn, omn, cn, sn, err2, h, t_new;
+        double Ax[7], Ay[7], xn, yn, thn, vxn, vyn, omn, cn, sn, err2, h, t_new, ipd[TR::NP];
         for (;;) {
             if (S.h_abs < min_step) return RK_FAILED;
             t_new = S.t + S.h_abs;
             if (t_new - T > 0) t_new = T;
             h = t_new - S.t;
             S.h_abs = fabs(h);
-            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
+            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2, pd, ipd);
             if (controller(err2, rejected, t_new < T, S.h_abs)) break;
         }
         rejected = false;
         double gn[TR::NEV];
-        event_values(c, e, xn, yn, omn, gn, pd);
+        event_values_from_pd<TR>(c, xn, yn, omn, pd, gn);
         const uint32_t active = active_events<TR>(g, gn);
         if (active) {
             fill_event_io<TR>(*io, e, S, h, Ax, Ay, active);

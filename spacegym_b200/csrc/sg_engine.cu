@@ -645,13 +645,13 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
         if (t_new - c.T > 0) t_new = c.T;
         h = t_new;
         S.h_abs = fabs(h);
-        double xn, yn, thn, vxn, vyn, omn, cn, sn, err2;
-        rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
+        double xn, yn, thn, vxn, vyn, omn, cn, sn, err2, ipd[TR::NP];
+        rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2, pd, ipd);
         if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
             kind = KIND_CONT;  // rejected: the attempt loop is resumed from the same state with the smaller step
         } else {
-            double gn[TR::NEV], ipd[TR::NP];
-            event_values_inv(c, e, xn, yn, omn, gn, pd, ipd);
+            double gn[TR::NEV];
+            event_values_from_pd<TR>(c, xn, yn, omn, pd, gn);
             active = active_events<TR>(g, gn);
             if (active) {
                 kind = KIND_EVENT;
@@ -794,14 +794,14 @@ __device__ __forceinline__ void cont1_entry(const DevCfg& c, uint32_t j, bool va
             if (t_new - c.T > 0) t_new = c.T;
             h = t_new - S.t;
             S.h_abs = fabs(h);
-            double xn, yn, thn, vxn, vyn, omn, cn, sn, err2;
-            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2);
+            double xn, yn, thn, vxn, vyn, omn, cn, sn, err2, ipd[TR::NP];
+            rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2, pd, ipd);
             if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
                 kind = KIND_CONT;
             } else {
                 rejected = false;
-                double gn[TR::NEV], ipd[TR::NP];
-                event_values_inv(c, e, xn, yn, omn, gn, pd, ipd);
+                double gn[TR::NEV];
+                event_values_from_pd<TR>(c, xn, yn, omn, pd, gn);
                 active = active_events<TR>(g, gn);
                 if (active) {
                     kind = KIND_EVENT;
