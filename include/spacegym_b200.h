@@ -42,7 +42,12 @@ extern "C" {
 #define SG_MAX_COLS 4
 #define SG_FREE_WORDS 4 /* free-tile multiset: 64 x 4-bit entries */
 
-enum sg_task { SG_TASK_GOAL = 0, SG_TASK_KEPLER = 1 };
+/* SG_TASK_DONOTCRASH: gym_space/envs/do_not_crash.py (one planet inside a circular border, observation
+ * [x, y, cos, sin, vx, vy, omega], reward 100/300 per step).  Upstream the class cannot be constructed
+ * (ShipParams is called without `steering`, do_not_crash.py:19-21); here `ship_steering` is a parameter like
+ * in the other tasks, default acceleration (the class sets a moment of inertia, which only that mode uses).
+ * Its planet / border use the kepler_planet_* / kepler_border_radius fields. */
+enum sg_task { SG_TASK_GOAL = 0, SG_TASK_KEPLER = 1, SG_TASK_DONOTCRASH = 2 };
 enum sg_steering { SG_STEER_ACCELERATION = 0, SG_STEER_VELOCITY = 1 }; /* ship_params.py:5-8 */
 enum sg_obs_dtype { SG_OBS_F64 = 0, SG_OBS_F32 = 1 };
 /* How sg_step maps onto kernels.  AUTO: K == 1 runs the split path (hot kernel + continuation and tail

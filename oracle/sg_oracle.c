@@ -32,6 +32,7 @@
 int so_obs_dim(const so_config* cfg) {
     /* spaceship_env.py:113-131, kepler.py:172-187 */
     if (cfg->task == SO_TASK_GOAL) return 7 + 2 * cfg->n_planets + 2;
+    if (cfg->task == SO_TASK_DONOTCRASH) return 7; /* with_lidar=False, with_goal=False (do_not_crash.py:30-31) */
     return 10;
 }
 
@@ -78,6 +79,17 @@ void so_config_finalize(so_config* cfg) {
             }
             cfg->goal_radius = cfg->ship_radius = pr / 2;
         }
+    } else if (cfg->task == SO_TASK_DONOTCRASH) {
+        /* do_not_crash.py:10-32 */
+        cfg->n_planets = 2;
+        cfg->planet_mass[0] = 6e8;
+        cfg->planet_radius[0] = 0.25;
+        cfg->planet_mass[1] = 0.0;
+        cfg->planet_radius[1] = 1.0;
+        cfg->world_size = 2 * 1.0;
+        cfg->step_size = 0.07;
+        cfg->max_abs_vel_angle = 5.0;
+        cfg->rows = cfg->cols = 0;
     } else {
         /* kepler.py:17-18,204-223 */
         cfg->n_planets = 2;
@@ -112,6 +124,19 @@ int so_config_from_id(const char* id, so_config* cfg) {
         cfg->goal_sparse_reward = 5.0;
         cfg->max_engine_force = 0.4;
         cfg->danger_zone = 0.25;
+        so_config_finalize(cfg);
+        return 0;
+    }
+    if (!strcmp(id, "DoNotCrashContinuous-v0") || !strcmp(id, "DoNotCrashDiscrete-v0")) {
+        /* gym_space/__init__.py:5-15, do_not_crash.py:19-21.  The reference omits ShipParams.steering
+         * (TypeError at construction); the golden fixtures were made with that one argument supplied
+         * (tests/golden/make_golden.py), default acceleration steering. */
+        cfg->task = SO_TASK_DONOTCRASH;
+        cfg->discrete = !strcmp(id, "DoNotCrashDiscrete-v0");
+        cfg->steering = 0;
+        cfg->ship_moi = 0.05;
+        cfg->max_engine_force = 0.3;
+        cfg->max_episode_steps = 300;
         so_config_finalize(cfg);
         return 0;
     }
@@ -534,7 +559,7 @@ void so_make_obs(const so_config* cfg, const so_env* env, double* obs) {
         for (int p = 0; p < P; ++p)
             lidar(y, env->planets + 2 * p, cfg->planet_radius[p], cfg->world_size, obs + 7 + 2 * p);
         lidar(y, env->goal, 0.0, cfg->world_size, obs + 7 + 2 * P);
-    } else {
+    } else if (cfg->task == SO_TASK_KEPLER) {
         obs[7] = env->orbit_angle;
         obs[8] = env->orbit_ecc;
         obs[9] = cfg->ref_orbit_a;
@@ -870,8 +895,25 @@ static void reset_kepler_env(const so_config* cfg, so_env* env, so_draws* d) {
     env->planets[0] = env->planets[1] = env->planets[2] = env->planets[3] = 0.0;
 }
 
+static void reset_donotcrash_env(const so_config* cfg, so_env* env, so_draws* d) {
+    /* do_not_crash.py:34-45 */
+    double pang = 0 + (SO_TWO_PI - 0) * so_next_uniform(d);
+    double lo = cfg->planet_radius[0] + 0.2, hi = cfg->planet_radius[1] - 0.15;
+    double dist = lo + (hi - lo) * so_next_uniform(d);
+    env->y[0] = cos(pang) * dist;
+    env->y[1] = sin(pang) * dist;
+    env->y[2] = 0 + (SO_TWO_PI - 0) * so_next_uniform(d);
+    env->y[3] = so_next_normal(d) * 0.07;
+    env->y[4] = so_next_normal(d) * 0.07;
+    double maxw = 0.7 * cfg->max_abs_vel_angle;
+    double w = so_next_normal(d) * maxw / 3;
+    env->y[5] = fmin(fmax(w, -maxw), maxw);
+    env->planets[0] = env->planets[1] = env->planets[2] = env->planets[3] = 0.0;
+}
+
 void so_reset(const so_config* cfg, so_env* env, so_draws* d) {
     if (cfg->task == SO_TASK_GOAL) reset_goal_env(cfg, env, d);
+    else if (cfg->task == SO_TASK_DONOTCRASH) reset_donotcrash_env(cfg, env, d);
     else reset_kepler_env(cfg, env, d);
     env->elapsed = 0;
     env->ep_return = 0.0;
@@ -908,6 +950,8 @@ int so_step(const so_config* cfg, so_env* env, const float* raw_action, so_draws
             reached = 1;
             if (draws) so_find_new_goal(cfg, env, draws);
         }
+    } else if (cfg->task == SO_TASK_DONOTCRASH) {
+        r = 100.0 / 300; /* do_not_crash.py:11,47-48: the class attribute max_episode_steps */
     } else {
         r = kepler_reward(cfg, env, act, is_f32);
     }

@@ -26,7 +26,7 @@ extern "C" {
 #define SO_MAX_FREE 64
 #define SO_MAX_OBS (9 + 2 * SO_MAX_PLANETS)
 
-enum { SO_TASK_GOAL = 0, SO_TASK_KEPLER = 1 };
+enum { SO_TASK_GOAL = 0, SO_TASK_KEPLER = 1, SO_TASK_DONOTCRASH = 2 }; /* goal.py, kepler.py, do_not_crash.py */
 enum { SO_STEER_ACCEL = 0, SO_STEER_VELOCITY = 1 }; /* gym_space/ship_params.py:5-8 */
 
 typedef struct so_config {

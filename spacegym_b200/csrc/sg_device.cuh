@@ -62,7 +62,45 @@ __device__ __forceinline__ double fast_div(double a, double b) {
     return fma(fma(-b, q, a), y, q);  // residual correction
 }
 
-enum { TASK_GOAL = 0, TASK_KEPLER = 1 };
+// ---- x^(1/5) and x^(-1/10) without pow ----------------------------------------------------------------
+// The step-size rules need (0.01 / d)^(1/5) (scipy:common.py:131) and err^(-1/5) = (err^2)^(-1/10)
+// (scipy:rk.py:150-161).  CUDA's pow is a ~200-instruction serial chain behind a CALL that a warp walks
+// whenever any of its lanes needs the value.  Here: float seed from MUFU.LG2/EX2 (relative error ~3e-7)
+// and two division-free Newton steps on the inverse root (quadratic: 3e-7 -> ~5e-13 -> < 1 ulp), i.e.
+// ~20 FP64 instructions with no branch.  Results agree with a correctly rounded pow to ~2 ulp.
+#ifndef SG_LIBM_POW
+__device__ __forceinline__ double fifth_root(double x) {  // x in [1e-30, 1e30]
+    double z = (double)exp2f(-0.2f * __log2f((float)x));  // z ~ x^(-1/5)
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double z2 = z * z, z4 = z2 * z2;
+        const double r = fma(-(x * z), z4, 1.0);  // 1 - x z^5
+        z = fma(z * 0.2, r, z);                   // Newton on z^-5 = x
+    }
+    const double z2 = z * z;
+    return x * (z2 * z2);  // x^(1/5) = x z^4
+}
+__device__ __forceinline__ double inv_tenth_root(double x) {  // x^(-1/10), x in [1e-30, 1e30]
+    double z = (double)exp2f(-0.1f * __log2f((float)x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+        const double r = fma(-(x * z2), z8, 1.0);  // 1 - x z^10
+        z = fma(z * 0.1, r, z);
+    }
+    return z;
+}
+#else
+__device__ __forceinline__ double fifth_root(double x) { return pow(x, 0.2); }
+__device__ __forceinline__ double inv_tenth_root(double x) { return pow(x, -0.1); }
+#endif
+// 0.9 * err^(-1/5) of the step-size controller, from err2 = err^2, clamped to the range in which the
+// caller's min(10, .) / max(0.2, .) can still depend on the value (outside it the clamp decides)
+__device__ __forceinline__ double controller_factor(double err2) {
+    return 0.9 * inv_tenth_root(fmin(fmax(err2, 1e-14), 1e10));
+}
+
+enum { TASK_GOAL = 0, TASK_KEPLER = 1, TASK_DNC = 2 };  // DNC: do_not_crash.py (Kepler-like scene, no orbit)
 enum { STEER_ACC = 0, STEER_VEL = 1 };
 
 // ---- Dormand-Prince tableau (scipy:rk.py:538-565), 1-based stage names ------------------
@@ -150,7 +188,9 @@ struct DevCfg {
     // Kepler
     double orbit_a, numC, radC, actC;
     float actC_f32;
-    double kep_lo, kep_hi;  // reset radius range (kepler.py:235-237)
+    double kep_lo, kep_hi;  // reset radius range (kepler.py:235-237, do_not_crash.py:36-38)
+    double reset_v_std, reset_om_div;  // reset velocity scale / omega divisor (kepler.py:262-265: 0.05, 5; do_not_crash.py:41-43: 0.07, 3)
+    double const_reward;               // DoNotCrash: 100 / max_episode_steps (do_not_crash.py:11,47-48)
 };
 
 // ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) ---------------------------------------
@@ -243,7 +283,7 @@ struct Traits {
     static constexpr int STEER = STEER_;
     static constexpr int DISC = DISC_;
     static constexpr int NEV = (TASK_ == TASK_GOAL ? NP_ : 2) + 3;   // events (dynamic_model.py:183-217)
-    static constexpr int D = TASK_ == TASK_GOAL ? 9 + 2 * NP_ : 10;  // observation length
+    static constexpr int D = TASK_ == TASK_GOAL ? 9 + 2 * NP_ : (TASK_ == TASK_KEPLER ? 10 : 7);  // observation length
 };
 
 template <class TR>
@@ -647,7 +687,7 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
         // (x -> x^5 is monotone), and pay for pow only on the lanes that need its value.
         const double l2 = lim * lim;
         if (0.01 >= dm * (l2 * l2 * lim) * 1.0000000001) h_abs = lim;
-        else h_abs = fmin(lim, pow(fast_div(0.01, dm), 0.2));
+        else h_abs = fmin(lim, fifth_root(fmax(fast_div(0.01, dm), 1e-30)));
     }
     S.h_abs = h_abs;
     event_values_from_pd<TR>(c, x, y, om, pd, g);
@@ -771,13 +811,13 @@ __device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t,
 __device__ __forceinline__ bool controller(double err2, bool& rejected, bool more_steps, double& h_abs) {
     if (err2 < 1) {
         if (more_steps) {  // the next step size only matters if another step follows
-            double factor = (err2 == 0) ? 10.0 : fmin(10.0, 0.9 * pow(err2, -0.1));
+            double factor = (err2 == 0) ? 10.0 : fmin(10.0, controller_factor(err2));
             if (rejected) factor = fmin(1.0, factor);
             h_abs *= factor;
         }
         return true;
     }
-    h_abs *= fmax(0.2, 0.9 * pow(err2, -0.1));
+    h_abs *= fmax(0.2, controller_factor(err2));
     rejected = true;
     return false;
 }
@@ -922,7 +962,7 @@ __device__ __forceinline__ void make_obs_inv(const DevCfg& c, const EnvRegs<TR>&
         }
         row[7 + 2 * TR::NP] = (OT)((e.gx - e.x) * c.two_over_ws);
         row[8 + 2 * TR::NP] = (OT)((e.gy - e.y) * c.two_over_ws);
-    } else {
+    } else if (TR::TASK == TASK_KEPLER) {
         row[7] = (OT)e.ang;
         row[8] = (OT)e.ecc;
         row[9] = (OT)c.orbit_a;
@@ -949,7 +989,7 @@ __device__ __forceinline__ void make_obs_cs(const DevCfg& c, const EnvRegs<TR>& 
         }
         row[7 + 2 * TR::NP] = (OT)((e.gx - e.x) * c.two_over_ws);
         row[8 + 2 * TR::NP] = (OT)((e.gy - e.y) * c.two_over_ws);
-    } else {
+    } else if (TR::TASK == TASK_KEPLER) {
         row[7] = (OT)e.ang;
         row[8] = (OT)e.ecc;
         row[9] = (OT)c.orbit_a;
@@ -1262,14 +1302,14 @@ __device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, 
         out[0] = cs * dist;
         out[1] = sn * dist;
         out[2] = kTwoPi * rng.uniform();
-        if (c.randomize) {
+        if (TR::TASK == TASK_KEPLER && c.randomize) {
             out[6] = rng.uniform() * 0.7;
             out[7] = rng.uniform() * 2 * kPi;
         }
-        out[3] = rng.normal() * 0.05;
-        out[4] = rng.normal() * 0.05;
+        out[3] = rng.normal() * c.reset_v_std;
+        out[4] = rng.normal() * c.reset_v_std;
         double maxw = 0.7 * c.om_max;
-        double w = rng.normal() * maxw / 5;
+        double w = rng.normal() * maxw / c.reset_om_div;
         out[5] = fmin(fmax(w, -maxw), maxw);
     }
 }

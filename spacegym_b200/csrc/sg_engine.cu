@@ -94,7 +94,7 @@ __device__ __forceinline__ void adopt_reset(const DevCfg& c, EnvRegs<TR>& e, con
         }
         e.gx = out[6 + 2 * TR::NP];
         e.gy = out[7 + 2 * TR::NP];
-    } else if (c.randomize) {
+    } else if (TR::TASK == TASK_KEPLER && c.randomize) {
         e.ecc = out[6];
         e.ang = out[7];
     }
@@ -187,8 +187,10 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
                 double cur;
                 r = goal_reward<TR>(c, e, lx, ly, pd, cur);
                 reached = cur < c.goal_radius;
-            } else {
+            } else if (TR::TASK == TASK_KEPLER) {
                 r = kepler_reward<TR>(c, e, act);
+            } else {
+                r = c.const_reward;  // do_not_crash.py:47-48
             }
             bool trunc = false;
             elapsed += 1;
@@ -322,6 +324,9 @@ __device__ __forceinline__ void warp_stats_flush(const DevCfg& c, double (&st)[4
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        // most warps end no episode and reach no goal in a step: one vote instead of a 5-deep dependent
+        // shuffle/add chain per counter (the chain is pure latency at the end of the warp's life)
+        if (!__any_sync(0xffffffffu, st[k] != 0)) continue;
         const double v = warp_sum(st[k]);
         if (lane == k && v != 0) atomicAdd(&c.stats[k], v);
     }
@@ -378,8 +383,10 @@ __device__ __forceinline__ void finish_env(const DevCfg& c, long long i, EnvRegs
             r += c.sparse;
             st[3] += 1;
         }
-    } else {
+    } else if (TR::TASK == TASK_KEPLER) {
         r = kepler_reward<TR>(c, e, act);
+    } else {
+        r = c.const_reward;  // do_not_crash.py:47-48
     }
     uint32_t elapsed = elapsed0 + 1;
     bool trunc = false;
@@ -520,6 +527,17 @@ enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2, KIND_FINISH = 3 };
 #endif
 #ifndef SG_CONT_MINB
 #define SG_CONT_MINB 3
+#endif
+// Grid sizes of the queue-driven kernels, in CTAs per SM (both walk their queue with a grid stride).  The queue
+// lengths are only known on the device, so the grids are sized for the resident capacity, not for the worst
+// case: a CTA that finds no work still has to wait for a slot with its registers (21 K / 15 K) next to the hot
+// CTAs of the other env batches in flight.  Measured, 8 batches of 262144 envs: 8/8 -> 4.16e9, 6/2 -> 4.50e9,
+// 3/2 -> 4.65e9, 3/1 -> 4.69e9, 2/1 -> 4.69e9 env-steps/s.
+#ifndef SG_CONT_GRID
+#define SG_CONT_GRID 3
+#endif
+#ifndef SG_TAIL_GRID
+#define SG_TAIL_GRID 1
 #endif
 // One chunk of kBlock envs through the common path.  `publish` = true (fused persistent kernel): a
 // continuation entry becomes visible to the in-kernel consumers by the release of its index word.
@@ -828,7 +846,10 @@ __device__ __forceinline__ void cont1_entry(const DevCfg& c, uint32_t j, bool va
     uint32_t s_cont, s_event, s_post;
     queue_push3(&c.q_counts[6], kind == KIND_CONT, &c.q_counts[1], kind == KIND_EVENT, &c.q_counts[2], need_post, s_cont,
                 s_event, s_post);
-    if (kind == KIND_CONT) save_cont<TR>(c, c.q_cont2, c.scr_cont2, s_cont, i, S, lx, ly, rejected);
+    if (kind == KIND_CONT) {
+        save_cont<TR>(c, c.q_cont2, c.scr_cont2, s_cont, i, S, lx, ly, rejected);
+        save_cont_scene<TR>(c, c.scr_cont2, s_cont, e, act);
+    }
     if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
     if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
 }
@@ -908,7 +929,6 @@ template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock, SG_CONT_MINB)
 cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out, int second_queue) {
-    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     const uint32_t count = second_queue ? c.q_counts[6] : c.q_counts[0];
     const uint32_t* q_in = second_queue ? c.q_cont2 : c.q_cont;
     const double* scr_in = second_queue ? c.scr_cont2 : c.scr_cont;
@@ -924,8 +944,8 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         if (valid) {
             i = q_in[j];
             EnvRegs<TR> e;
-            load_env<TR>(c, i, e);
-            const Act act = fetch_action<TR>(c, actions, i, step0);
+            Act act;
+            load_cont_scene<TR>(c, scr_in, j, e, act);  // planets / goal / action terms: coalesced scratch rows, no gather
             bool rejected;
             const uint32_t elapsed0 = c.elapsed[i];
             const double ep_ret0 = c.ep_return[i];
@@ -965,7 +985,10 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
 }
 
 // terminal events (dense output + Brent roots + epilogue + reset) and the post work of finished envs
-constexpr int kTailBlock = 64;
+#ifndef SG_TAIL_BLOCK
+#define SG_TAIL_BLOCK 64
+#endif
+constexpr int kTailBlock = SG_TAIL_BLOCK;
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kTailBlock)
 tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
@@ -1257,6 +1280,15 @@ extern "C" int sg_config_finalize(sg_config* cfg) {
         cfg->rows = cfg->cols = 0;
         cfg->planets_radius = cfg->kepler_planet_radius;
         cfg->goal_radius = cfg->ship_radius = 0;
+    } else if (cfg->task == SG_TASK_DONOTCRASH) {
+        // do_not_crash.py:10-32: planet and border at the origin, world = the border's bounding square
+        cfg->n_planets = 2;
+        cfg->world_size = 2 * cfg->kepler_border_radius;
+        cfg->max_abs_vel_angle = 5.0;
+        cfg->step_size = 0.07;
+        cfg->rows = cfg->cols = 0;
+        cfg->planets_radius = cfg->kepler_planet_radius;
+        cfg->goal_radius = cfg->ship_radius = 0;
     } else {
         return SG_ERR_INVALID;
     }
@@ -1297,6 +1329,19 @@ extern "C" int sg_config_from_id(const char* id, sg_config* cfg) {
         if (disc) cfg->max_engine_force = 1;
         return sg_config_finalize(cfg);
     }
+    if (!strcmp(id, "DoNotCrashContinuous-v0") || !strcmp(id, "DoNotCrashDiscrete-v0")) {
+        // gym_space/__init__.py:5-15, do_not_crash.py:10-32.  Upstream omits ShipParams.steering (TypeError);
+        // default here: acceleration steering (the class sets moi = 0.05, which only that mode uses).
+        cfg->task = SG_TASK_DONOTCRASH;
+        cfg->discrete = !strcmp(id, "DoNotCrashDiscrete-v0");
+        cfg->max_episode_steps = 300;
+        cfg->ship_steering = SG_STEER_ACCELERATION;
+        cfg->ship_moi = 0.05;
+        cfg->max_engine_force = 0.3;
+        cfg->kepler_planet_radius = 0.25;
+        cfg->kepler_border_radius = 1.0;
+        return sg_config_finalize(cfg);
+    }
     cfg->task = SG_TASK_KEPLER;  // gym_space/__init__.py:76-146
     cfg->rad_penalty_C = 2;
     cfg->numerator_C = 0.01;
@@ -1327,7 +1372,8 @@ extern "C" int sg_config_from_id(const char* id, sg_config* cfg) {
 
 extern "C" int sg_obs_dim(const sg_config* cfg) {
     if (!cfg) return SG_ERR_INVALID;
-    return cfg->task == SG_TASK_GOAL ? 9 + 2 * cfg->n_planets : 10;
+    if (cfg->task == SG_TASK_GOAL) return 9 + 2 * cfg->n_planets;
+    return cfg->task == SG_TASK_KEPLER ? 10 : 7;  // kepler.py:172-187 appends the orbit; do_not_crash.py has no lidar / goal
 }
 
 extern "C" int sg_state_layout(const sg_config* cfg, int64_t n, sg_layout* out) {
@@ -1424,8 +1470,18 @@ static void build_dev(sg_env* h) {
     d.radC = c.rad_penalty_C;
     d.actC = c.act_penalty_C;
     d.actC_f32 = (float)c.act_penalty_C;
-    d.kep_lo = c.kepler_planet_radius + 0.5;  // kepler.py:235-237
-    d.kep_hi = c.kepler_border_radius - 0.5;
+    if (c.task == SG_TASK_DONOTCRASH) {
+        d.kep_lo = c.kepler_planet_radius + 0.2;  // do_not_crash.py:36-38
+        d.kep_hi = c.kepler_border_radius - 0.15;
+        d.reset_v_std = 0.07;                     // do_not_crash.py:41-43
+        d.reset_om_div = 3;
+    } else {
+        d.kep_lo = c.kepler_planet_radius + 0.5;  // kepler.py:235-237
+        d.kep_hi = c.kepler_border_radius - 0.5;
+        d.reset_v_std = 0.05;                     // kepler.py:262-265
+        d.reset_om_div = 5;
+    }
+    d.const_reward = 100.0 / 300;  // do_not_crash.py:11,47-48 (the class attribute, not the TimeLimit in force)
     // sub-batches: same constants, base pointers shifted by the sub-batch offset, own queue block
     char* q = (char*)h->d_queues;
     for (int s = 0; s < h->n_sub; ++s) {
@@ -1670,9 +1726,9 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         const long long off = sb.off;
         const int sms = h->sm_count > 0 ? h->sm_count : 148;
         const int hot_blocks = (int)((sb.n + kBlock - 1) / kBlock);
-        const int cont_blocks = hot_blocks < sms * 8 ? hot_blocks : sms * 8;
+        const int cont_blocks = hot_blocks < sms * SG_CONT_GRID ? hot_blocks : sms * SG_CONT_GRID;
         const long long tb = (sb.n + kTailBlock - 1) / kTailBlock;
-        const int tail_blocks = (int)(tb < sms * 8 ? tb : sms * 8);
+        const int tail_blocks = (int)(tb < sms * SG_TAIL_GRID ? tb : sms * SG_TAIL_GRID);
         const float* act = a.actions ? a.actions + 2 * off : nullptr;
         OT* obs = a.obs ? (OT*)a.obs + off * TR::D : nullptr;
         double* rew = a.reward ? a.reward + off : nullptr;
@@ -1756,11 +1812,19 @@ static void launch_np(const sg_env* h, const LaunchArgs& a) {
 
 // enqueue only (no error query: also used inside stream capture)
 static int enqueue(sg_env* h, const LaunchArgs& a) {
+#ifdef SG_DEV_ONLY_GOAL3P  // development builds (seconds instead of minutes): the BASELINE workload's instantiation only
+    if (h->cfg.task == SG_TASK_GOAL && h->cfg.n_planets == 3 && h->cfg.ship_steering == SG_STEER_VELOCITY &&
+        !h->cfg.discrete && h->cfg.obs_dtype != SG_OBS_F32 && a.op != OP_VFIELD)
+        launch_typed<Traits<TASK_GOAL, 3, STEER_VEL, 0>, double>(h, a);
+    else return fail(h, SG_ERR_INVALID, "SG_DEV_ONLY_GOAL3P build: only GoalContinuous3P-v0 / f64 observations");
+#else
     if (h->cfg.task == SG_TASK_KEPLER) launch_np<TASK_KEPLER, 1>(h, a);
+    else if (h->cfg.task == SG_TASK_DONOTCRASH) launch_np<TASK_DNC, 1>(h, a);
     else if (h->cfg.n_planets == 2) launch_np<TASK_GOAL, 2>(h, a);
     else if (h->cfg.n_planets == 3) launch_np<TASK_GOAL, 3>(h, a);
     else if (h->cfg.n_planets == 4) launch_np<TASK_GOAL, 4>(h, a);
     else return fail(h, SG_ERR_INVALID, "unsupported n_planets");
+#endif
     h->launches += (a.op == OP_STEP_SPLIT) ? ((h->use_cont1 && !h->use_fused) ? 4 : 3) : 1;
     return SG_OK;
 }

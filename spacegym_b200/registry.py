@@ -13,7 +13,10 @@ GOAL_IDS = ("GoalContinuous2P-v0", "GoalContinuous3P-v0", "GoalContinuous4P-v0",
             "GoalDiscrete2-v0", "GoalDiscrete3-v0", "GoalDiscrete4-v0")
 KEPLER_IDS = ("KeplerCircleOrbit-v0", "KeplerEllipseEasy-v0", "KeplerEllipseHard-v0", "KeplerRandomOrbits-v0",
               "KeplerDiscrete-v0")
-ENV_IDS = GOAL_IDS + KEPLER_IDS
+# do_not_crash.py / gym_space/__init__.py:5-15.  Upstream the constructor raises TypeError (ShipParams without
+# `steering`); here `ship_steering` is a keyword like in the other tasks (default 0 = acceleration).
+DONOTCRASH_IDS = ("DoNotCrashContinuous-v0", "DoNotCrashDiscrete-v0")
+ENV_IDS = GOAL_IDS + KEPLER_IDS + DONOTCRASH_IDS
 
 # reference kwargs -> sg_config field (None: accepted and ignored, as in the reference)
 _GOAL_KW = {
@@ -28,6 +31,7 @@ _KEPLER_KW = {
     "rad_penalty_C": "rad_penalty_C", "act_penalty_C": "act_penalty_C", "step_size": "step_size",
     "ship_steering": "ship_steering", "ship_moi": "ship_moi", "max_engine_force": "max_engine_force",
 }
+_DONOTCRASH_KW = {"ship_steering": "ship_steering"}  # DoNotCrashEnv.__init__ takes no kwargs upstream
 # engine-level options (not in the reference constructors)
 _ENGINE_KW = {"max_episode_steps": "max_episode_steps", "auto_reset": "auto_reset", "discrete": "discrete",
               "obs_dtype": "obs_dtype", "step_mode": "step_mode"}
@@ -39,7 +43,7 @@ def make_config(env_id, **kwargs):
     if rc == -4:
         raise KeyError(f"No registered env with id: {env_id}")
     check(rc)
-    table = dict(_GOAL_KW if cfg.task == 0 else _KEPLER_KW)
+    table = dict((_GOAL_KW, _KEPLER_KW, _DONOTCRASH_KW)[cfg.task])
     table.update(_ENGINE_KW)
     for k, v in kwargs.items():
         if k not in table:

@@ -85,9 +85,12 @@ class BatchedSpaceEnv:
             hi = [1.0, 1.0, 1.0, 1.0, np.inf, np.inf, 1.0] + 2 * (self.cfg.n_planets + 1) * [2 * np.sqrt(2)]
             hi = np.array(hi, dtype=np.float32)
             self.single_observation_space = spaces.Box(-hi, hi)
-        else:
+        elif self.cfg.task == 1:
             hi = np.array([1.0, 1.0, 1.0, 1.0, np.inf, np.inf, 1.0, 2 * np.pi, 0.7, 2])
             self.single_observation_space = spaces.Box(-hi, hi, np.dtype(np.float64))
+        else:  # DoNotCrash: with_lidar=False, with_goal=False (do_not_crash.py:30-31)
+            hi = np.array([1.0, 1.0, 1.0, 1.0, np.inf, np.inf, 1.0], dtype=np.float32)
+            self.single_observation_space = spaces.Box(-hi, hi)
         self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
 
     # ---- helpers --------------------------------------------------------------------------------
@@ -236,7 +239,7 @@ class BatchedSpaceEnv:
             v["col_shift"] = self._field(lay.col_shift, c.cols, torch.float64)
             v["free_tiles"] = self._field(lay.free_tiles, 4, torch.int64)
             v["tile_word"] = self._field(lay.tile_word, 1, torch.int32)
-        else:
+        elif c.task == 1:
             v["orbit"] = self._field(lay.orbit, 2, torch.float64)
         return v
 

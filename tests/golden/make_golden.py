@@ -60,7 +60,25 @@ CASES = {
     "kepler_random": ("KeplerRandomOrbits-v0", {}),
     "goal3p_discrete": ("<GoalDiscrete>", GOAL_DISCRETE_KW),
     "kepler_discrete": ("<KeplerDiscrete>", KEPLER_DISCRETE_KW),
+    # DoNotCrash cannot be constructed upstream: do_not_crash.py:19-21 calls ShipParams without its first field
+    # `steering` (TypeError).  The fixtures supply exactly that one argument and nothing else (make_donotcrash).
+    "donotcrash": ("<DoNotCrashContinuous>", {"ship_steering": 0}),
+    "donotcrash_vel": ("<DoNotCrashContinuous>", {"ship_steering": 1}),
+    "donotcrash_discrete": ("<DoNotCrashDiscrete>", {"ship_steering": 0}),
 }
+
+
+def make_donotcrash(discrete, ship_steering):
+    import functools
+
+    import gym_space.envs.do_not_crash as dnc
+    from gym_space.ship_params import ShipParams, Steering
+    saved = dnc.ShipParams
+    dnc.ShipParams = functools.partial(ShipParams, Steering(ship_steering))  # the missing positional argument
+    try:
+        return (dnc.DoNotCrashDiscreteEnv if discrete else dnc.DoNotCrashContinuousEnv)()
+    finally:
+        dnc.ShipParams = saved
 
 
 def make_env(case):
@@ -70,6 +88,8 @@ def make_env(case):
             env = GoalDiscreteEnv(**kw)
         elif env_id == "<KeplerDiscrete>":
             env = KeplerDiscreteEnv(**kw)
+        elif env_id.startswith("<DoNotCrash"):
+            env = make_donotcrash(env_id == "<DoNotCrashDiscrete>", **kw)
         else:
             env = gym.make(env_id, **kw).unwrapped
     return env
@@ -98,7 +118,7 @@ def is_goal(env):
 
 
 def orbit_of(env):
-    if is_goal(env):
+    if is_goal(env) or not hasattr(env, "ref_orbit_angle"):
         return np.zeros(3)
     return np.array([env.ref_orbit_angle, env.ref_orbit_eccentricity, env.ref_orbit_a], dtype=np.float64)
 
@@ -141,7 +161,7 @@ def harvest_transitions(case, n_steps, n_keep, seed):
         )
         recs.append(rec)
         t_ep += 1
-        if done or t_ep >= 500:
+        if done or t_ep >= getattr(env, "max_episode_steps", 500):
             env.reset()
             t_ep = 0
     # category-balanced selection
@@ -285,7 +305,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"transitions_{case}.npz"), **tr)
         print(case, "transitions", len(tr["reward"]), "done", int(tr["done"].sum()), "goal",
               int(tr["goal_reached"].sum()), "multi", int((tr["n_steps"] >= 2).sum()), flush=True)
-    for ci, case in enumerate(("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random")):
+    for ci, case in enumerate(("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random", "donotcrash")):
         if only and case not in only:
             continue
         rs = harvest_resets(case, 64, seed=5000 + ci)

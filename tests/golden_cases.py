@@ -19,9 +19,13 @@ CASES = {
     # keyboard_agent.py:10-58 (discrete variants)
     "goal3p_discrete": ("GoalContinuous3P-v0", {"discrete": 1, "max_engine_force": 1.0}),
     "kepler_discrete": ("KeplerCircleOrbit-v0", {"discrete": 1}),
+    # do_not_crash.py with the missing `steering` argument supplied (make_golden.py: make_donotcrash)
+    "donotcrash": ("DoNotCrashContinuous-v0", {}),
+    "donotcrash_vel": ("DoNotCrashContinuous-v0", {"ship_steering": 1}),
+    "donotcrash_discrete": ("DoNotCrashDiscrete-v0", {}),
 }
 
-RESET_CASES = ("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random")
+RESET_CASES = ("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random", "donotcrash")
 
 # the parity bar: |delta| <= TOL * max(1, |ref|)  (BASELINE.json north_star: 1e-9 in FP64)
 TOL = 1e-9

@@ -51,6 +51,16 @@ def test_registry_matches_reference_kwargs():
         assert lib().sg_obs_dim(C.byref(cfg)) == 10
     cfg = sg.make_config("KeplerEllipseHard-v0", randomize=True, ship_steering=0)  # BASELINE config 4
     assert cfg.randomize == 1 and cfg.ship_steering == 0
+    for env_id, disc in (("DoNotCrashContinuous-v0", 0), ("DoNotCrashDiscrete-v0", 1)):  # do_not_crash.py:10-32
+        cfg = sg.make_config(env_id)
+        assert (cfg.task, cfg.discrete, cfg.ship_steering, cfg.ship_moi, cfg.max_engine_force, cfg.max_thruster_force,
+                cfg.world_size, cfg.max_abs_vel_angle, cfg.step_size, cfg.max_episode_steps,
+                cfg.kepler_planet_radius, cfg.kepler_border_radius) == (2, disc, 0, 0.05, 0.3, 0.05, 2.0, 5.0, 0.07,
+                                                                        300, 0.25, 1.0)
+        assert lib().sg_obs_dim(C.byref(cfg)) == 7
+    assert sg.make_config("DoNotCrashContinuous-v0", ship_steering=1).ship_steering == 1
+    with pytest.raises(TypeError):
+        sg.make_config("DoNotCrashContinuous-v0", n_planets=2)
 
 
 def test_registry_error_behaviour():

@@ -32,7 +32,7 @@ def test_transitions_match_reference_golden(case, mode):
     if env.cfg.task == 0:
         st["planets"] = g["planets"].reshape(n, -1)
         st["goal"] = g["goal"]
-    else:
+    elif env.cfg.task == 1:
         st["orbit"] = np.stack([g["orbit"][:, 1], g["orbit"][:, 0]], axis=1)  # golden: (angle, ecc, a)
     env.set_state(st)
     obs, rew, done, _ = env.step(to_dev(g["action"]))
@@ -49,8 +49,9 @@ def test_transitions_match_reference_golden(case, mode):
 
 
 LOCKSTEP = [(c, "split") for c in ("goal2p", "goal3p", "goal4p", "goal3p_accel", "kepler_circle",
-                                    "kepler_hard_accel_rand", "goal3p_discrete", "kepler_discrete")]
-LOCKSTEP += [(c, "fused") for c in ("goal3p", "goal2p", "kepler_hard_accel_rand", "goal3p_discrete")]
+                                    "kepler_hard_accel_rand", "goal3p_discrete", "kepler_discrete", "donotcrash",
+                                    "donotcrash_vel", "donotcrash_discrete")]
+LOCKSTEP += [(c, "fused") for c in ("goal3p", "goal2p", "kepler_hard_accel_rand", "goal3p_discrete", "donotcrash")]
 
 
 @pytest.mark.parametrize("case,mode", LOCKSTEP)
@@ -359,3 +360,36 @@ def test_config5_goal4p_4m_envs_sharded(oracle):
     assert tot > 0.01 * 31 * 2 * n * 0.5
     for e in shards:
         e.close()
+
+
+@pytest.mark.parametrize("env_id", ["GoalContinuous3P-v0", "DoNotCrashContinuous-v0"])
+def test_trajectory_dump_and_headless_replay(env_id, tmp_path):
+    """recorded state -> .npz -> software-rendered frames (gym_space/rendering.py geometry)."""
+    n, T = 64, 40
+    env = sg.make(env_id, n, seed=11)
+    rec = sg.TrajectoryRecorder(env, indices=[3, 17])
+    env.reset()
+    rec.start()
+    rng = np.random.RandomState(0)
+    for t in range(T):
+        a = to_dev(rng.uniform(-1, 1, size=(n, 2)).astype(np.float32))
+        obs, rew, done, _ = env.step(a)
+        rec.record(a, rew, done)
+    path = rec.save(str(tmp_path / "traj.npz"))
+    d = np.load(path)
+    assert d["ship"].shape == (T + 1, 2, 6) and d["action"].shape == (T, 2, 2) and d["done"].shape == (T, 2)
+    assert close(d["ship"][-1], env.get_state()["ship"].cpu().numpy()[[3, 17]]).all()
+    assert (d["action"][..., 0] >= 0).all() and (d["action"][..., 0] <= 1).all()  # engine in [0, 1]
+    frames = sg.replay(path, env_slot=1, every=4)
+    assert frames.shape == (11, 600, 600, 3) and frames.dtype == np.uint8
+    # the ship disc sits where the recorded state says (white inside a dark outline)
+    ws = float(d["world_size"])
+    x, y = (d["ship"][-1, 1, :2] + ws / 2) * (600 / ws)  # T is a multiple of `every`: the last frame is the last state
+    f = frames[-1]
+    if 20 < x < 580 and 20 < y < 580:
+        yy, xx = np.mgrid[-10:11, -10:11]
+        disc = f[599 - int(y) + yy, int(x) + xx][(yy ** 2 + xx ** 2) <= 100]
+        assert (disc == 255).all(axis=1).mean() > 0.6  # white body; the trace and the middle point are drawn over it
+        ring = [f[599 - int(y + 15 * np.sin(k)), int(x + 15 * np.cos(k))].max() for k in np.linspace(2, 4.3, 12)]
+        assert min(ring) < 170
+    env.close()
