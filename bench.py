@@ -8,9 +8,12 @@ Workload (BASELINE.json configs[2], the config the north-star target is quoted o
 GoalContinuous3P-v0, 262144 envs per step and per GPU, auto-reset with hexagonal-tiling
 placement, TimeLimit 500, uniform random float32 actions.  A "step" is one env.step() of one
 batch of 262144 envs (one `sg_step` launch, K=1: actions read from HBM, observation, reward
-and done written to HBM).  Eight independent env batches (each on its own stream) are stepped
-round-robin, so that the working set (8 x 100 MB state+outputs) exceeds the 126 MB L2 between revisits
+and done written to HBM).  Sixteen independent env batches (each on its own stream) are stepped
+round-robin, so that the working set (16 x 100 MB state+outputs) exceeds the 126 MB L2 between revisits
 and the latency-bound continuation / tail kernels of one batch overlap the hot kernel of another.
+CUDA_DEVICE_MAX_CONNECTIONS is raised to 32 (unless the caller set it): with the default of 8 hardware
+queues, more than 8 streams alias onto the same queue and serialise (measured: 8 batches 4.94e9,
+16 batches 4.31e9 at 8 connections, 5.09e9 at 32).
 
 Prints ONE JSON line (rank 0).  `value` = device-timed (CUDA events, max over ranks) whole-job
 env-steps/s with inputs resident in HBM; `e2e` = the same through BatchedSpaceEnv.step with
@@ -30,13 +33,15 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before the CUDA context exists; see the module doc
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENV_ID = "GoalContinuous3P-v0"
 ENV_KW = {}
 ENVS_PER_STEP = 262144
-N_BATCHES = 8
+N_BATCHES = 16
 ACTION_SETS = 4
 # SURVEY.md §8d contract figures for GoalContinuous3P-v0 (per env step, K=1, f64 observation)
 ALGO_BYTES_PER_STEP = 329.0
@@ -435,7 +440,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm", type=int, default=128, help="untimed env steps per batch (one fused-kernel launch) that bring the envs to their steady-state mix of episode ages before warm-up")
-    ap.add_argument("--batches", type=int, default=None, help="independent env batches in flight (default 8)")
+    ap.add_argument("--batches", type=int, default=None, help="independent env batches in flight (default 16)")
     ap.add_argument("--no-f32", action="store_true", help="skip the float32-observation end-to-end leg")
     ap.add_argument("--env-id", default=None, help="benchmark another registered id (default: the BASELINE workload)")
     ap.add_argument("--kwargs", default="{}", help="JSON dict of reference-style kwargs for --env-id")

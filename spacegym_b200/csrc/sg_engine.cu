@@ -25,30 +25,48 @@ namespace sg {
 constexpr int kBlock = 128;
 
 // ---- state access ---------------------------------------------------------------------------
+#ifndef SG_LD_MODE
+#define SG_LD_MODE 0
+#endif
+// State rows are read once per kernel.  0 (default): plain loads.  1: ld.global.cs (streaming).  2:
+// ld.global.L1::no_allocate.  Measured (8 batches of 262144 envs): 4.97e9 / 4.81e9 / 4.84e9 env-steps/s — the
+// hot kernel alone is indifferent (39.4 / 40.4 / 39.5 us), the kernels that follow it gather by env index and
+// like the rows cached.
+__device__ __forceinline__ double ld_row(const double* p) {
+#if SG_LD_MODE == 2
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#elif SG_LD_MODE == 1
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
 template <class TR>
 __device__ __forceinline__ void load_env(const DevCfg& c, long long i, EnvRegs<TR>& e) {
     const long long n = c.stride;
-    e.x = c.ship[i];
-    e.y = c.ship[n + i];
-    e.th = c.ship[2 * n + i];
-    e.vx = c.ship[3 * n + i];
-    e.vy = c.ship[4 * n + i];
-    e.om = c.ship[5 * n + i];
+    e.x = ld_row(c.ship + i);
+    e.y = ld_row(c.ship + n + i);
+    e.th = ld_row(c.ship + 2 * n + i);
+    e.vx = ld_row(c.ship + 3 * n + i);
+    e.vy = ld_row(c.ship + 4 * n + i);
+    e.om = ld_row(c.ship + 5 * n + i);
     if (TR::TASK == TASK_GOAL) {
 #pragma unroll
         for (int p = 0; p < TR::NP; ++p) {
-            e.px[p] = c.planets[(2 * p) * n + i];
-            e.py[p] = c.planets[(2 * p + 1) * n + i];
+            e.px[p] = ld_row(c.planets + (2 * p) * n + i);
+            e.py[p] = ld_row(c.planets + (2 * p + 1) * n + i);
         }
-        e.gx = c.goal[i];
-        e.gy = c.goal[n + i];
+        e.gx = ld_row(c.goal + i);
+        e.gy = ld_row(c.goal + n + i);
         e.ecc = e.ang = 0.0;
     } else {
         e.px[0] = 0.0;  // kepler.py:204-206: planet and border sit at the origin
         e.py[0] = 0.0;
         e.gx = e.gy = 0.0;
-        e.ecc = c.orbit[i];
-        e.ang = c.orbit[n + i];
+        e.ecc = (TR::TASK == TASK_KEPLER) ? ld_row(c.orbit + i) : 0.0;
+        e.ang = (TR::TASK == TASK_KEPLER) ? ld_row(c.orbit + n + i) : 0.0;
     }
 }
 
@@ -290,13 +308,28 @@ __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Queue atomics as inline PTX.  Written as atomicAdd() inside `if (lane == 0)`, the compiler substitutes its
+// own warp-aggregation sequence (VOTEU / ATOMG / SHFL.IDX) whose shuffle consumes the result on the spot, so
+// the L2 round trip is waited for where the atomic is issued (and a second atomic only starts after the
+// first returned).  The asm form returns into a register that nothing reads until the slot is needed.
+__device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned long long atom_add_u64(void* p, unsigned long long v) {
+    unsigned long long old;
+    asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+
 // warp-aggregated queue append; must be called by all 32 lanes of the warp
 __device__ __forceinline__ uint32_t queue_push(uint32_t* counter, bool need) {
     const unsigned mask = __ballot_sync(0xffffffffu, need);
     if (mask == 0) return 0;
     const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
     uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    if (lane == leader) base = atom_add_u32(counter, (uint32_t)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
@@ -309,9 +342,9 @@ __device__ __forceinline__ void queue_push3(uint32_t* c0, bool n0, uint32_t* c1,
     const int lane = threadIdx.x & 31;
     uint32_t b0 = 0, b1 = 0, b2 = 0;
     if (lane == 0) {
-        if (m0) b0 = atomicAdd(c0, (uint32_t)__popc(m0));
-        if (m1) b1 = atomicAdd(c1, (uint32_t)__popc(m1));
-        if (m2) b2 = atomicAdd(c2, (uint32_t)__popc(m2));
+        if (m0) b0 = atom_add_u32(c0, (uint32_t)__popc(m0));
+        if (m1) b1 = atom_add_u32(c1, (uint32_t)__popc(m1));
+        if (m2) b2 = atom_add_u32(c2, (uint32_t)__popc(m2));
     }
     const unsigned below = (1u << lane) - 1u;
     s0 = __shfl_sync(0xffffffffu, b0, 0) + (uint32_t)__popc(m0 & below);
@@ -520,7 +553,7 @@ __device__ __forceinline__ void save_event(const DevCfg& c, uint32_t slot, long 
     p[22 * cap] = lx; p[23 * cap] = ly; p[24 * cap] = (double)active;
 }
 
-enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2, KIND_FINISH = 3 };
+enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2, KIND_FINISH = 3, KIND_CONT_REJECTED = 4 };
 
 #ifndef SG_HOT_MINB
 #define SG_HOT_MINB 4
@@ -624,7 +657,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
                                           OT* __restrict__ obs, double* __restrict__ reward,
                                           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                           long long block_first, OT* sobs, double (&st)[4], bool publish,
-                                          const Stage<TR>* stage = nullptr) {
+                                          const Stage<TR>* stage = nullptr, double* stash = nullptr) {
     constexpr int D = TR::D;
     const long long i = block_first + threadIdx.x;
     const bool valid = i < c.n;
@@ -648,14 +681,24 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
             act = translate_action<TR>(c, r0, r1);
         }
     } else if (valid) {
+        // What only the epilogue needs (episode return / length so far, last_xy) is parked in the thread's own
+        // shared-memory slots for the duration of the integration instead of in registers: the two counters go
+        // global -> shared without touching a register (cp.async).  Held in registers they were spilled to local
+        // memory and came back from L2 (a long-scoreboard wait at the reload).
+        reinterpret_cast<volatile uint32_t*>(&stash[1 * kBlock + threadIdx.x])[1] = 0u;  // see the queue atomic below
+        cp_async8(&stash[0 * kBlock + threadIdx.x], c.ep_return + i);
+        cp_async4(&stash[1 * kBlock + threadIdx.x], c.elapsed + i);
+        cp_async_commit();
         load_env<TR>(c, i, e);
         act = fetch_action<TR>(c, actions, i, step0);
-        elapsed0 = c.elapsed[i];  // fetched with the state: not on the critical path of the epilogue
-        ep_ret0 = c.ep_return[i];
+        stash[2 * kBlock + threadIdx.x] = e.x;  // env.last_xy (spaceship_env.py:74)
+        stash[3 * kBlock + threadIdx.x] = e.y;
     }
     if (valid) {
-        lx = e.x;
-        ly = e.y;  // env.last_xy (spaceship_env.py:74)
+        if (STAGED) {
+            lx = e.x;
+            ly = e.y;
+        }
         double g[TR::NEV], pd[TR::NP];
         init_step<TR>(c, e, act, S, g, pd);
         // first _step_impl attempt (scipy:rk.py:111-143); t = 0
@@ -666,7 +709,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
         double xn, yn, thn, vxn, vyn, omn, cn, sn, err2, ipd[TR::NP];
         rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2, pd, ipd);
         if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
-            kind = KIND_CONT;  // rejected: the attempt loop is resumed from the same state with the smaller step
+            kind = KIND_CONT_REJECTED;  // the attempt loop is resumed from the same state with the smaller step
         } else {
             double gn[TR::NEV];
             event_values_from_pd<TR>(c, xn, yn, omn, pd, gn);
@@ -690,14 +733,28 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     }
     // queue appends at warp-converged points.  The continuation / event atomics are issued BEFORE the
     // epilogue of the finished lanes, whose arithmetic then covers the L2 round trip of the atomics.
-    const unsigned m_cont = __ballot_sync(0xffffffffu, kind == KIND_CONT);
+    const bool is_cont = kind == KIND_CONT || kind == KIND_CONT_REJECTED;
+    const unsigned m_cont = __ballot_sync(0xffffffffu, is_cont);
     const unsigned m_event = __ballot_sync(0xffffffffu, kind == KIND_EVENT);
     const int lane = threadIdx.x & 31;
-    uint32_t b_cont = 0, b_event = 0;
-    if (lane == 0) {
-        if (m_cont) b_cont = atomicAdd(&c.q_counts[0], (uint32_t)__popc(m_cont));
-        if (m_event) b_event = atomicAdd(&c.q_counts[1], (uint32_t)__popc(m_event));
+    uint32_t opaque_zero = 0;
+    if (!STAGED) opaque_zero = reinterpret_cast<volatile uint32_t*>(&stash[1 * kBlock + threadIdx.x])[1];
+    if (!STAGED && valid) {
+        cp_async_wait<0>();
+        ep_ret0 = stash[0 * kBlock + threadIdx.x];
+        elapsed0 = *reinterpret_cast<const uint32_t*>(&stash[1 * kBlock + threadIdx.x]);
+        lx = stash[2 * kBlock + threadIdx.x];
+        ly = stash[3 * kBlock + threadIdx.x];
     }
+    // q_counts[0] (continuation) and [1] (event) are one aligned 64-bit word: one atomic reserves both.  The
+    // operand carries a term that is zero at run time (a word this thread parked in shared memory) but
+    // lane-dependent as far as ptxas can tell: with a provably warp-uniform operand it rewrites even an inline-PTX atom into its own
+    // elect / ATOMG / SHFL.IDX sequence, and that shuffle waits for the L2 round trip right here instead of
+    // after the epilogue below.
+    unsigned long long b_both = 0;
+    if (lane == 0 && (m_cont | m_event))
+        b_both = atom_add_u64(c.q_counts, ((unsigned long long)__popc(m_cont) | ((unsigned long long)__popc(m_event) << 32)) +
+                                              (unsigned long long)opaque_zero);
     if (kind == KIND_FINISH) {
         uint32_t status = 0;
         commit_state<TR>(e, fx, fy, fth, fvx, fvy, fom, status);
@@ -708,11 +765,12 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
         kind = KIND_DONE;
     }
     const unsigned below = (1u << lane) - 1u;
-    const uint32_t s_cont = __shfl_sync(0xffffffffu, b_cont, 0) + (uint32_t)__popc(m_cont & below);
-    const uint32_t s_event = __shfl_sync(0xffffffffu, b_event, 0) + (uint32_t)__popc(m_event & below);
+    b_both = __shfl_sync(0xffffffffu, b_both, 0);
+    const uint32_t s_cont = (uint32_t)b_both + (uint32_t)__popc(m_cont & below);
+    const uint32_t s_event = (uint32_t)(b_both >> 32) + (uint32_t)__popc(m_event & below);
     const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
-    if (kind == KIND_CONT) {
-        save_cont<TR>(c, c.q_cont, c.scr_cont, s_cont, i, S, lx, ly, rejected, !publish);
+    if (is_cont) {
+        save_cont<TR>(c, c.q_cont, c.scr_cont, s_cont, i, S, lx, ly, kind == KIND_CONT_REJECTED, !publish);
         save_cont_scene<TR>(c, c.scr_cont, s_cont, e, act);
         if (publish) st_release(c.q_cont + s_cont, (uint32_t)i);  // scratch row visible before "ready"
     }
@@ -735,8 +793,10 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
     const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     __shared__ __align__(16) OT sobs[kBlock * TR::D];
+    __shared__ double stash[4 * kBlock];
     double st[4] = {0, 0, 0, 0};
-    hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)blockIdx.x * kBlock, sobs, st, false);
+    hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)blockIdx.x * kBlock, sobs, st, false,
+                      nullptr, stash);
     warp_stats_flush(c, st);
 }
 
@@ -882,6 +942,7 @@ fused_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
     const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     __shared__ __align__(16) OT sobs[kBlock * TR::D];
     __shared__ uint32_t s_ticket;
+    __shared__ double stash[4 * kBlock];
     double st[4] = {0, 0, 0, 0};
     for (;;) {  // phase 1
         if (threadIdx.x == 0) s_ticket = atomicAdd(&c.q_counts[7], 1u);
@@ -889,7 +950,8 @@ fused_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
         const uint32_t chunk = s_ticket;
         __syncthreads();
         if (chunk >= n_chunks) break;
-        hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)chunk * kBlock, sobs, st, true);
+        hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)chunk * kBlock, sobs, st, true,
+                          nullptr, stash);
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -981,7 +1043,7 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         }
         if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
     }
-    block_stats_flush<kBlock>(c, st);
+    warp_stats_flush(c, st);  // no block barrier: a warp leaves as soon as its own entries are done
 }
 
 // terminal events (dense output + Brent roots + epilogue + reset) and the post work of finished envs
@@ -1059,9 +1121,10 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         // instruction once per warp, so its time is largely instruction-fetch latency)
         if (do_post) post_env<TR, OT>(c, post_i, post_reached, post_done, obs);
     }
-    block_stats_flush<kTailBlock>(c, st);
+    warp_stats_flush(c, st);
     // the last block to finish empties the queues for the next step
     __shared__ bool last;
+    __syncthreads();  // every warp of the block is done before the block takes its ticket
     __threadfence();
     if (threadIdx.x == 0) last = (atomicAdd(&c.q_counts[3], 1u) == gridDim.x - 1);
     __syncthreads();
