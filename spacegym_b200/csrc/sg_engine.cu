@@ -141,7 +141,23 @@ __device__ __forceinline__ void flush_obs_warp(const OT* sobs, OT* obs, long lon
     const long long first = block_first + 32 * warp;
     long long rows = n - first;
     if (rows <= 0) return;
-    if (rows > 32) rows = 32;
+    if (rows >= 32) {
+        // full warp (every warp but possibly the last of the grid): compile-time trip count, 32-bit indices, all
+        // shared-memory loads in flight before the first store
+        constexpr int NVEC = 32 * D * (int)sizeof(OT) / 16;
+        static_assert((32 * D * sizeof(OT)) % 16 == 0, "a warp's rows are a whole number of 16-byte vectors");
+        constexpr int IT = (NVEC + 31) / 32;
+        const int4* s4 = reinterpret_cast<const int4*>(sobs + 32 * warp * D);
+        int4* d4 = reinterpret_cast<int4*>(obs + first * D);
+        int4 v[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k)
+            if (k * 32 + lane < NVEC) v[k] = s4[k * 32 + lane];
+#pragma unroll
+        for (int k = 0; k < IT; ++k)
+            if (k * 32 + lane < NVEC) d4[k * 32 + lane] = v[k];
+        return;
+    }
     const long long total = rows * D;             // elements
     const OT* src = sobs + 32 * warp * D;          // 16-byte aligned: 32 * D * sizeof(OT) is a multiple of 16
     OT* dst = obs + first * D;
@@ -583,6 +599,7 @@ struct Stage {
     static constexpr int NF = (TR::TASK == TASK_GOAL ? 6 + 2 * TR::NP + 2 : 6 + 2) + 2;  // + ep_return + action
     double f[NF][kBlock];
     uint32_t elapsed[kBlock];
+    uint32_t zero[kBlock];  // written once by its thread; see the queue atomic in hot_chunk
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
@@ -623,7 +640,7 @@ __device__ __forceinline__ void stage_prefetch(const DevCfg& c, const float* __r
 
 template <class TR>
 __device__ __forceinline__ void stage_load(const DevCfg& c, const Stage<TR>& s, bool have_actions, EnvRegs<TR>& e,
-                                           float& r0, float& r1, uint32_t& elapsed0, double& ep_ret0) {
+                                           float& r0, float& r1) {
     const int t = threadIdx.x;
     int k = 0;
     e.x = s.f[k++][t]; e.y = s.f[k++][t]; e.th = s.f[k++][t]; e.vx = s.f[k++][t]; e.vy = s.f[k++][t]; e.om = s.f[k++][t];
@@ -642,14 +659,13 @@ __device__ __forceinline__ void stage_load(const DevCfg& c, const Stage<TR>& s, 
         e.ecc = s.f[k++][t];
         e.ang = s.f[k++][t];
     }
-    ep_ret0 = s.f[k++][t];
+    k++;  // ep_return: read from the stage when the epilogue needs it
     r0 = r1 = 0.0f;
     if (have_actions) {
         const float2 a = *reinterpret_cast<const float2*>(&s.f[k][t]);
         r0 = a.x;
         r1 = a.y;
     }
-    elapsed0 = s.elapsed[t];
 }
 
 template <class TR, typename OT, bool STAGED = false>
@@ -674,8 +690,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     double ep_ret0 = 0.0;
     if (STAGED) {
         float r0 = 0.0f, r1 = 0.0f;
-        if (valid) stage_load<TR>(c, *stage, actions != nullptr, e, r0, r1, elapsed0, ep_ret0);
-        __syncthreads();  // the stage buffer is reused as the observation staging area of this chunk
+        if (valid) stage_load<TR>(c, *stage, actions != nullptr, e, r0, r1);
         if (valid) {
             if (!actions) random_action(c.seed, (unsigned long long)(c.first_env + i), step0, TR::DISC != 0, r0, r1);
             act = translate_action<TR>(c, r0, r1);
@@ -695,10 +710,6 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
         stash[3 * kBlock + threadIdx.x] = e.y;
     }
     if (valid) {
-        if (STAGED) {
-            lx = e.x;
-            ly = e.y;
-        }
         double g[TR::NEV], pd[TR::NP];
         init_step<TR>(c, e, act, S, g, pd);
         // first _step_impl attempt (scipy:rk.py:111-143); t = 0
@@ -738,13 +749,23 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     const unsigned m_event = __ballot_sync(0xffffffffu, kind == KIND_EVENT);
     const int lane = threadIdx.x & 31;
     uint32_t opaque_zero = 0;
-    if (!STAGED) opaque_zero = reinterpret_cast<volatile uint32_t*>(&stash[1 * kBlock + threadIdx.x])[1];
-    if (!STAGED && valid) {
-        cp_async_wait<0>();
-        ep_ret0 = stash[0 * kBlock + threadIdx.x];
-        elapsed0 = *reinterpret_cast<const uint32_t*>(&stash[1 * kBlock + threadIdx.x]);
-        lx = stash[2 * kBlock + threadIdx.x];
-        ly = stash[3 * kBlock + threadIdx.x];
+    if (STAGED) {  // the stage still holds this chunk's inputs: x, y are rows 0, 1, ep_return the row before the action
+        opaque_zero = *reinterpret_cast<const volatile uint32_t*>(&stage->zero[threadIdx.x]);
+        if (valid) {
+            ep_ret0 = stage->f[Stage<TR>::NF - 2][threadIdx.x];
+            elapsed0 = stage->elapsed[threadIdx.x];
+            lx = stage->f[0][threadIdx.x];
+            ly = stage->f[1][threadIdx.x];
+        }
+    } else {
+        opaque_zero = reinterpret_cast<volatile uint32_t*>(&stash[1 * kBlock + threadIdx.x])[1];
+        if (valid) {
+            cp_async_wait<0>();
+            ep_ret0 = stash[0 * kBlock + threadIdx.x];
+            elapsed0 = *reinterpret_cast<const uint32_t*>(&stash[1 * kBlock + threadIdx.x]);
+            lx = stash[2 * kBlock + threadIdx.x];
+            ly = stash[3 * kBlock + threadIdx.x];
+        }
     }
     // q_counts[0] (continuation) and [1] (event) are one aligned 64-bit word: one atomic reserves both.  The
     // operand carries a term that is zero at run time (a word this thread parked in shared memory) but
@@ -777,13 +798,8 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
     if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
     if (obs) {  // rows of queued envs are rewritten by the later kernels
-        if (STAGED) {
-            __syncthreads();
-            flush_obs<OT, D>(sobs, obs, block_first, c.n);
-        } else {
-            __syncwarp();
-            flush_obs_warp<OT, D>(sobs, obs, block_first, c.n);
-        }
+        __syncwarp();
+        flush_obs_warp<OT, D>(sobs, obs, block_first, c.n);
     }
 }
 
@@ -814,31 +830,41 @@ __device__ __forceinline__ void load_cont(const DevCfg& c, const double* scr, ui
     S.fs = act.fs;
 }
 
-// Persistent form of the hot kernel (default): gridDim = resident CTAs, each walks chunks blockIdx.x, + gridDim.x,
-// ... with the next chunk's inputs in flight (cp.async, two stages) while the current one is integrated.
+// Pipelined form of the hot kernel: gridDim = resident CTAs, each walks the chunks blockIdx.x, + gridDim.x, ...
+// Every thread copies the inputs of ITS env of the next chunk global -> shared (cp.async, two stage buffers)
+// while it integrates the current one, so only the first chunk of a CTA waits for DRAM (in the one-chunk kernel
+// that wait is 12 % of a warp's life).  A thread only ever reads shared memory it wrote itself: no block
+// barrier anywhere.  Dynamic shared memory: 2 stages + the observation staging rows.
+template <class TR, typename OT>
+struct HotPipeSmem {
+    Stage<TR> stages[2];
+    alignas(16) OT sobs[kBlock * TR::D];
+};
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
 hot_staged_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
                   uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out, uint32_t n_chunks) {
     const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
-    __shared__ __align__(16) Stage<TR> stages[2];
-    static_assert(sizeof(Stage<TR>) >= sizeof(OT) * kBlock * TR::D, "a consumed stage doubles as the obs staging area");
-    double st[4] = {0, 0, 0, 0};
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HotPipeSmem<TR, OT>& sm = *reinterpret_cast<HotPipeSmem<TR, OT>*>(smem_raw);
+    sm.stages[0].zero[threadIdx.x] = 0u;
+    sm.stages[1].zero[threadIdx.x] = 0u;
     uint32_t chunk = blockIdx.x;
     int cur = 0;
-    if (chunk < n_chunks) stage_prefetch<TR>(c, actions, (long long)chunk * kBlock + threadIdx.x, stages[0]);
+    if (chunk < n_chunks) stage_prefetch<TR>(c, actions, (long long)chunk * kBlock + threadIdx.x, sm.stages[0]);
     cp_async_commit();
     for (; chunk < n_chunks; chunk += gridDim.x, cur ^= 1) {
         const uint32_t next = chunk + gridDim.x;
-        if (next < n_chunks) stage_prefetch<TR>(c, actions, (long long)next * kBlock + threadIdx.x, stages[cur ^ 1]);
+        if (next < n_chunks) stage_prefetch<TR>(c, actions, (long long)next * kBlock + threadIdx.x, sm.stages[cur ^ 1]);
         cp_async_commit();
         cp_async_wait<1>();  // everything but the group just committed has landed: this chunk's inputs
-        hot_chunk<TR, OT, true>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)chunk * kBlock,
-                                reinterpret_cast<OT*>(&stages[cur]), st, false, &stages[cur]);
-        __syncthreads();  // the rows staged in stages[cur] are flushed before the next prefetch overwrites them
+        double st[4] = {0, 0, 0, 0};  // per chunk: nothing but the loop counters is live across chunks
+        hot_chunk<TR, OT, true>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)chunk * kBlock, sm.sobs, st,
+                                false, &sm.stages[cur]);
+        warp_stats_flush(c, st);
+        __syncwarp();  // the warp's observation rows are flushed before its lanes stage the next chunk's rows
     }
     cp_async_wait<0>();
-    block_stats_flush<kBlock>(c, st);
 }
 
 // One more Runge-Kutta attempt for continuation entry j of the first queue (valid = the entry exists).
@@ -1804,7 +1830,16 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
             fused_kernel<TR, OT><<<fused_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
         } else if (h->use_staged) {
             int pblocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
-            hot_staged_kernel<TR, OT><<<pblocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
+            static bool attr_set = false;  // per instantiation
+            if (!attr_set) {
+                cudaFuncSetAttribute(hot_staged_kernel<TR, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(HotPipeSmem<TR, OT>));
+                cudaFuncSetAttribute(hot_staged_kernel<TR, OT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
+                attr_set = true;
+            }
+            hot_staged_kernel<TR, OT><<<pblocks, kBlock, sizeof(HotPipeSmem<TR, OT>), a.stream>>>(sb.dev, act, obs, rew, dn, tr,
+                                                                                             (uint32_t)hot_blocks);
         } else {
             hot_kernel<TR, OT><<<hot_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
         }

@@ -259,7 +259,7 @@ def test_full_size_rollout_properties():
     env.close()
 
 
-@pytest.mark.parametrize("plan", ["SG_CONT1", "SG_FUSED", "SG_SUBBATCHES"])
+@pytest.mark.parametrize("plan", ["SG_CONT1", "SG_FUSED", "SG_SUBBATCHES", "SG_STAGED"])
 def test_alternative_step_plans_match_oracle(oracle, plan, monkeypatch):
     """The other launch plans of the split path (single-attempt continuation kernel, fused persistent
     hot+continuation kernel with in-kernel queue consumption, concurrent sub-batches replayed as a CUDA
