@@ -184,6 +184,11 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (spacegym_b200 has no CPU path; use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: anything a library prints at the C level (NCCL's version banner when
+    # NCCL_DEBUG is set in the environment) is sent to stderr; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -412,7 +417,8 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     for e in envs:
         e.close()
     if world > 1:

@@ -5,6 +5,6 @@ layer that mirrors the reference's gym interface.  Nothing here imports the CPU 
 """
 from .registry import ENV_IDS, make_config  # noqa: F401
 from .vector_env import BatchedSpaceEnv, allreduce_stats, make, shard_range  # noqa: F401
-from .rendering import Renderer, TrajectoryRecorder, replay, write_png  # noqa: F401  (off the hot path: debugging aid)
+from .replay import Renderer, TrajectoryRecorder, replay, write_png  # noqa: F401  (off the hot path: debugging aid)
 
 __version__ = "0.1.0"

@@ -665,8 +665,10 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     q = S.Ax * rvx; S1 = fma(q, q, S1);
     q = S.Ay * rvy; S1 = fma(q, q, S1);
     q = alpha * rom; S1 = fma(q, q, S1);
-    double d0 = fast_sqrt0(S0) * kInvSqrt6, d1 = fast_sqrt0(S1) * kInvSqrt6;
-    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : fast_div(0.01 * d0, d1);
+    // select_initial_step on the SQUARES of its norms (d0^2 = S0 / 6, d1^2 = S1 / 6, d2^2 = S2 / (6 h0^2)): every
+    // comparison of scipy:common.py:118-132 is monotone in the norm, h0 = 0.01 d0 / d1 = 0.01 sqrt(S0 / S1) needs
+    // one reciprocal and one square root instead of two square roots and a division, and d2 is never divided out.
+    double h0 = (S0 < 6e-10 || S1 < 6e-10) ? 1e-6 : 0.01 * fast_sqrt(S0 * fast_rcp(S1));
     h0 = fmin(h0, T);
     double Bx, By, cn, sn;
     const double dprobe = h0 * om;
@@ -676,18 +678,19 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     q = h0 * alpha * rth; S2 = fma(q, q, S2);
     q = (Bx - S.Ax) * rvx; S2 = fma(q, q, S2);
     q = (By - S.Ay) * rvy; S2 = fma(q, q, S2);
-    double d2 = fast_div(fast_sqrt0(S2) * kInvSqrt6, h0);
-    const double dm = fmax(d1, d2);
+    const double hq = 6.0 * (h0 * h0);
+    const double M = fmax(S1 * (h0 * h0), S2);  // = 6 h0^2 max(d1, d2)^2
     const double lim = fmin(100 * h0, T);
     double h_abs;
-    if (d1 <= 1e-15 && d2 <= 1e-15) {
+    if (S1 <= 6e-30 && S2 <= 1e-30 * hq) {  // d1 <= 1e-15 and d2 <= 1e-15
         h_abs = fmin(lim, fmax(1e-6, h0 * 1e-3));
     } else {
-        // h1 = (0.01 / dm) ** 0.2 only matters when it is below lim: decide that without the pow
-        // (x -> x^5 is monotone), and pay for pow only on the lanes that need its value.
-        const double l2 = lim * lim;
-        if (0.01 >= dm * (l2 * l2 * lim) * 1.0000000001) h_abs = lim;
-        else h_abs = fmin(lim, fifth_root(fmax(fast_div(0.01, dm), 1e-30)));
+        // h1 = (0.01 / dm) ** 0.2 only matters when it is below lim: decide that without the root
+        // (0.01 >= dm lim^5  <=>  1e-4 * 6 h0^2 >= M lim^10), and pay for it only on the lanes that need its value:
+        // h1 = (dm^2 / 1e-4) ** (-1/10).
+        const double l2 = lim * lim, l5 = l2 * l2 * lim;
+        if (1e-4 * hq >= M * (l5 * l5) * 1.0000000002) h_abs = lim;
+        else h_abs = fmin(lim, inv_tenth_root(fmin(fmax(fast_div(1e4 * M, hq), 1e-30), 1e30)));
     }
     S.h_abs = h_abs;
     event_values_from_pd<TR>(c, x, y, om, pd, g);
@@ -733,14 +736,16 @@ __device__ __forceinline__ void small_sincos_n(const double (&d)[N], bool small,
             pc[j] = fma(pc[j], d2[j], -0.5);
             cs[j] = fma(pc[j], d2[j], 1.0);
         }
-    } else {  // |increment| >= 0.5 rad: only states injected from outside (|omega| > omega_max)
-        static_assert(N == 6, "slow path is written for the six stage headings");
-        const SinCos6 r = slow_sincos6(d[0], d[1], d[2], d[3], d[4], d[5]);
+    } else if (N == 6) {  // |increment| >= 0.5 rad: only states injected from outside (|omega| > omega_max)
+        const SinCos6 r = slow_sincos6(d[0], d[1 % N], d[2 % N], d[3 % N], d[4 % N], d[5 % N]);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             sn[j] = r.s[j];
             cs[j] = r.c[j];
         }
+    } else {  // shorter batches are only ever called with small == true
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) sincos_cold(d[j], &sn[j], &cs[j]);
     }
 }
 
@@ -762,7 +767,26 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     d[3] = c5 * ho + cs5 * ha;
     d[4] = ho + cs6 * ha;
     d[5] = ho + cs7 * ha;
-    small_sincos_n<6>(d, small, sd, cd);
+    if (TR::STEER == STEER_VEL && small) {
+        // velocity steering: alpha = 0, so the increments are c_i h omega with c = 1/5, 3/10, 4/5, 8/9, 1, 1.
+        // Three polynomials (a = d[0], d[1], d[3]) instead of six: 4a by two angle doublings, 5a = 4a + a by one
+        // rotation, and the last two headings coincide (d[4] == d[5] bit for bit: c4 == 4 c2 exactly and ha == 0).
+        const double dd[3] = {d[0], d[1], d[3]};
+        double s3[3], c3[3];
+        small_sincos_n<3>(dd, true, s3, c3);
+        sd[0] = s3[0]; cd[0] = c3[0];
+        sd[1] = s3[1]; cd[1] = c3[1];
+        sd[3] = s3[2]; cd[3] = c3[2];
+        const double s2 = 2.0 * (s3[0] * c3[0]), c2a = fma(-2.0 * s3[0], s3[0], 1.0);  // sin 2a, cos 2a
+        sd[2] = 2.0 * (s2 * c2a);
+        cd[2] = fma(-2.0 * s2, s2, 1.0);
+        sd[4] = fma(sd[2], c3[0], cd[2] * s3[0]);
+        cd[4] = fma(cd[2], c3[0], -(sd[2] * s3[0]));
+        sd[5] = sd[4];
+        cd[5] = cd[4];
+    } else {
+        small_sincos_n<6>(d, small, sd, cd);
+    }
     double cr[6], sr[6];  // stage headings: the base heading rotated by d[j]
 #pragma unroll
     for (int j = 0; j < 6; ++j) {

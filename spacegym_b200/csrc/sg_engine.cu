@@ -22,7 +22,10 @@
 
 namespace sg {
 
-constexpr int kBlock = 128;
+#ifndef SG_KBLOCK
+#define SG_KBLOCK 128
+#endif
+constexpr int kBlock = SG_KBLOCK;  // threads per CTA of every kernel but the tail kernel
 
 // ---- state access ---------------------------------------------------------------------------
 #ifndef SG_LD_MODE
@@ -1086,26 +1089,39 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
     const uint32_t total = n_event + n_post;
     const long long cap = c.q_cap;
     double st[4] = {0, 0, 0, 0};
+    // The event record (25 scratch rows) goes global -> shared with cp.async, every copy in flight at once, into
+    // the thread's own EventIO slot; handle_events works on it through the pointer.  Filled through registers the
+    // record lives on the local stack and the compiler pairs every load with its stack store, i.e. 25 serialised
+    // memory round trips (30 % of this kernel's stall samples).
+    __shared__ __align__(16) EventIO<TR> s_io[kTailBlock];
+    __shared__ double s_tail[3][kTailBlock];  // lx, ly, active
     for (uint32_t base = blockIdx.x * kTailBlock; base < total; base += gridDim.x * kTailBlock) {
         const uint32_t j = base + threadIdx.x;
         long long post_i = 0;
         bool post_reached = false, post_done = false, do_post = false;
         if (j < n_event) {
+            const double* p = c.scr_event + j;
+            EventIO<TR>& io = s_io[threadIdx.x];
+            cp_async8(&io.x, p + 0 * cap); cp_async8(&io.y, p + 1 * cap); cp_async8(&io.th, p + 2 * cap);
+            cp_async8(&io.vx, p + 3 * cap); cp_async8(&io.vy, p + 4 * cap); cp_async8(&io.om, p + 5 * cap);
+            cp_async8(&io.h, p + 6 * cap); cp_async8(&io.t_old, p + 7 * cap);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                cp_async8(&io.Ax[k], p + (8 + k) * cap);
+                cp_async8(&io.Ay[k], p + (15 + k) * cap);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) cp_async8(&s_tail[k][threadIdx.x], p + (22 + k) * cap);
+            cp_async_commit();
             const long long i = c.q_event[j];
             EnvRegs<TR> e;
             load_env<TR>(c, i, e);
             const Act act = fetch_action<TR>(c, actions, i, step0);
-            const double* p = c.scr_event + j;
-            EventIO<TR> io;
-            io.x = p[0 * cap]; io.y = p[1 * cap]; io.th = p[2 * cap]; io.vx = p[3 * cap]; io.vy = p[4 * cap];
-            io.om = p[5 * cap]; io.h = p[6 * cap]; io.t_old = p[7 * cap];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                io.Ax[k] = p[(8 + k) * cap];
-                io.Ay[k] = p[(15 + k) * cap];
-            }
-            const double lx = p[22 * cap], ly = p[23 * cap];
-            io.active = (uint32_t)p[24 * cap];
+            const uint32_t elapsed0 = c.elapsed[i];  // gathered with the state, used by the epilogue
+            const double ep_ret0 = c.ep_return[i];
+            cp_async_wait<0>();
+            const double lx = s_tail[0][threadIdx.x], ly = s_tail[1][threadIdx.x];
+            io.active = (uint32_t)s_tail[2][threadIdx.x];
             io.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
 #pragma unroll
             for (int q = 0; q < TR::NP; ++q) {
@@ -1125,8 +1141,8 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
             double ipd[TR::NP];
 #pragma unroll
             for (int q = 0; q < TR::NP; ++q) ipd[q] = fast_rcp(pd[q]);
-            finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, true, want_row ? row : nullptr, cs, sn, c.elapsed[i],
-                               c.ep_return[i], reward, done_out, trunc_out, st, reached, done);
+            finish_env<TR, OT>(c, i, e, act, lx, ly, pd, ipd, true, want_row ? row : nullptr, cs, sn, elapsed0, ep_ret0,
+                               reward, done_out, trunc_out, st, reached, done);
             if (want_row) {
 #pragma unroll
                 for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];

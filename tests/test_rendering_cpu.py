@@ -1,4 +1,4 @@
-"""CPU: the headless software renderer (spacegym_b200/rendering.py) draws the reference's scene
+"""CPU: the headless software renderer (spacegym_b200/replay.py) draws the reference's scene
 (gym_space/rendering.py): planet outlines, goal cross, ship disc, thrust-dependent exhaust, decaying trace."""
 import importlib.util
 import os
@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-spec = importlib.util.spec_from_file_location("sg_rendering", os.path.join(ROOT, "spacegym_b200", "rendering.py"))
+spec = importlib.util.spec_from_file_location("sg_rendering", os.path.join(ROOT, "spacegym_b200", "replay.py"))
 R = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(R)
 
