@@ -184,6 +184,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (spacegym_b200 has no CPU path; use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus = sg.bind_host_to_gpu(local) if world > 1 else os.sched_getaffinity(0)  # NUMA-local pinned buffers per rank
     # stdout carries exactly one JSON line: anything a library prints at the C level (NCCL's version banner when
     # NCCL_DEBUG is set in the environment) is sent to stderr; the line itself goes to the saved descriptor
     sys.stdout.flush()
@@ -412,6 +413,7 @@ def run_b200(args):
                     "steps": e2e_steps, "api": "BatchedSpaceEnv.step_async(numpy)/step_wait() -> sg_step_host_async/sg_host_wait, all env batches in flight"},
             "e2e_f32obs": e2e32,
             "gpu_launches": launches * world,
+            "host_cpus_rank0": len(cpus),
             "clocks": clocks,
             "episode_stats": stats,
         }

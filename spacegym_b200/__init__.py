@@ -4,7 +4,7 @@ Product package: CUDA kernels + C ABI (csrc/, include/spacegym_b200.h) and the P
 layer that mirrors the reference's gym interface.  Nothing here imports the CPU oracle.
 """
 from .registry import ENV_IDS, make_config  # noqa: F401
-from .vector_env import BatchedSpaceEnv, allreduce_stats, make, shard_range  # noqa: F401
+from .vector_env import BatchedSpaceEnv, allreduce_stats, bind_host_to_gpu, make, shard_range  # noqa: F401
 from .replay import Renderer, TrajectoryRecorder, replay, write_png  # noqa: F401  (off the hot path: debugging aid)
 
 __version__ = "0.1.0"

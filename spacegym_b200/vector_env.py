@@ -23,6 +23,26 @@ def shard_range(total_envs, rank, world_size):
     return start, base + (1 if rank < rem else 0)
 
 
+def bind_host_to_gpu(device_index):
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (intersected with the CPUs
+    the process may use), so that the pinned staging buffers of the host-buffer path are first-touched on, and
+    copied by threads of, the GPU's own NUMA node.  One process per GPU: call it before the first env is made.
+    Returns the CPU set in effect (unchanged if NVML or the intersection gives nothing)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        if local & allowed:
+            os.sched_setaffinity(0, local & allowed)
+    except Exception:  # no NVML / not permitted: keep the inherited affinity
+        pass
+    return os.sched_getaffinity(0)
+
+
 def allreduce_stats(vals):
     """Sum the 4-double episode statistics over torch.distributed ranks — the engine's only collective
     (SURVEY.md §8e).  NCCL needs the tensor on the GPU; gloo (CPU tests) reduces it in place."""
