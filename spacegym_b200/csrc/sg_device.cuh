@@ -541,7 +541,7 @@ __device__ double brent_root(const DevCfg& c, const EventIO<TR>& io, const Dense
 
 // scipy:ivp.py:683-697: roots of all active events, earliest one terminates; state := sol(t*)
 template <class TR>
-__device__ __noinline__ void handle_events(const DevCfg& c, EventIO<TR>* io) {
+static __device__ __noinline__ void handle_events(const DevCfg& c, EventIO<TR>* io) {
     Dense<TR> d;
     d.x0 = io->x; d.y0 = io->y; d.th0 = io->th; d.vx0 = io->vx; d.vy0 = io->vy; d.om0 = io->om;
     d.alpha = io->alpha; d.h = io->h; d.t_old = io->t_old;
@@ -697,12 +697,12 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
 }
 
 // out-of-line sincos for the cold paths (reset placement, terminal states): one copy of the range reduction
-__device__ __noinline__ void sincos_cold(double a, double* s, double* c) { sincos(a, s, c); }
+static __device__ __noinline__ void sincos_cold(double a, double* s, double* c) { sincos(a, s, c); }
 
 struct SinCos6 {
     double s[6], c[6];
 };
-__device__ __noinline__ SinCos6 slow_sincos6(double d0, double d1, double d2, double d3, double d4, double d5) {
+static __device__ __noinline__ SinCos6 slow_sincos6(double d0, double d1, double d2, double d3, double d4, double d5) {
     SinCos6 r;
     const double d[6] = {d0, d1, d2, d3, d4, d5};
 #pragma unroll 1
@@ -1139,7 +1139,7 @@ __device__ inline void store_tiles(const DevCfg& c, long long i, const Tiles& t,
 }
 
 // HexagonalTiling._tile_center_pos (hexagonal_tiling.py:136-158)
-__device__ __noinline__ void tile_center(const DevCfg& c, const Tiles& t, int tile, double& ox, double& oy) {
+static __device__ __noinline__ void tile_center(const DevCfg& c, const Tiles& t, int tile, double& ox, double& oy) {
     int row = tile / c.cols, col = tile % c.cols;
     double zero_x = -c.ws / 2 + c.hex_width / 2;
     double zero_y = c.ws / 2 - c.hex_height / 2;
@@ -1188,7 +1188,7 @@ __device__ inline void choice_no_replace(Rng& rng, int n, int k, int (&out)[KMAX
 }
 
 // HexagonalTiling.find_new_goal (hexagonal_tiling.py:95-134)
-__device__ __noinline__ void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double& gx, double& gy, uint32_t& status) {
+static __device__ __noinline__ void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double& gx, double& gy, uint32_t& status) {
     if (t.goal_tile != 63u) {
         if (t.n_free < 64u) {
             t.set(t.n_free, t.ship_tile);
@@ -1235,7 +1235,7 @@ __device__ __noinline__ void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, 
 
 // Goal resample on a reached goal (goal.py:155-157): cold, touches the tile state in HBM.
 template <class TR>
-__device__ __noinline__ void resample_goal(const DevCfg& c, long long i, Rng* rng, double* gxy, uint32_t* status) {
+static __device__ __noinline__ void resample_goal(const DevCfg& c, long long i, Rng* rng, double* gxy, uint32_t* status) {
     Tiles t;
     load_tiles(c, i, t);
     find_new_goal(c, t, *rng, gxy[0], gxy[1], *status);
@@ -1246,7 +1246,7 @@ __device__ __noinline__ void resample_goal(const DevCfg& c, long long i, Rng* rn
 // out: x, y, th, vx, vy, om; Goal: planets (x0, y0, ...) at [6..], goal at [6+2P]; Kepler: (ecc, ang) at [6..7]
 // when randomize (left untouched otherwise).
 template <class TR>
-__device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, double* out, uint32_t* status) {
+static __device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, double* out, uint32_t* status) {
     Rng& rng = *rngp;
     if (TR::TASK == TASK_GOAL) {
         constexpr int P = TR::NP;

@@ -20,6 +20,15 @@
 #include "../../include/spacegym_b200.h"
 #include "sg_device.cuh"
 
+// SG_PART: the library can be built as five translation units compiled in parallel (spacegym_b200/build.py):
+// part 0 = C ABI + dispatch + the 2-planet GoalEnv kernels, parts 1-4 = the kernels of one more env family each
+// (Goal 3P, Goal 4P, Kepler, DoNotCrash).  Without SG_PART the whole engine is one translation unit.
+#if defined(SG_PART) && SG_PART != 0
+#define SG_MAIN_PART 0
+#else
+#define SG_MAIN_PART 1
+#endif
+
 namespace sg {
 
 #ifndef SG_KBLOCK
@@ -1178,9 +1187,11 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
     }
 }
 
+#if SG_MAIN_PART
 __global__ void set_step_counter_kernel(uint32_t* q_counts, unsigned long long value) {
     *reinterpret_cast<unsigned long long*>(q_counts + 4) = value;
 }
+#endif
 
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock)
@@ -1233,6 +1244,7 @@ vector_field_kernel(const DevCfg c, const float* __restrict__ actions, double* _
     out[i * 6 + 5] = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
 }
 
+#if SG_MAIN_PART
 __global__ void fill_orbit_kernel(double* orbit, long long n, double ecc, double ang) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -1256,6 +1268,8 @@ __global__ void dfma_peak_kernel(double* out, int iters, double seed) {
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
 }
+
+#endif  // SG_MAIN_PART
 
 }  // namespace sg
 
@@ -1319,6 +1333,7 @@ struct sg_env {
     size_t s_k;
 };
 
+#if SG_MAIN_PART
 static thread_local std::string g_create_error;
 
 static int fail(sg_env* env, int code, const std::string& msg) {
@@ -1801,6 +1816,8 @@ extern "C" int sg_debug_kernel_times(sg_env* h, double out[6], int reset) {
     return SG_OK;
 }
 
+#endif  // SG_MAIN_PART
+
 // ---- kernel dispatch over (task, planets, steering, action space, obs dtype) -------------------
 enum Op { OP_STEP, OP_STEP_SPLIT, OP_RESET, OP_VFIELD };
 
@@ -1915,7 +1932,7 @@ static void launch_tr(const sg_env* h, const LaunchArgs& a) {
 }
 
 template <int TASK, int NP>
-static void launch_np(const sg_env* h, const LaunchArgs& a) {
+void launch_np(const sg_env* h, const LaunchArgs& a) {
     const bool vel = h->cfg.ship_steering == SG_STEER_VELOCITY;
     const bool disc = h->cfg.discrete != 0;
     if (vel && !disc) launch_tr<Traits<TASK, NP, STEER_VEL, 0>>(h, a);
@@ -1924,6 +1941,24 @@ static void launch_np(const sg_env* h, const LaunchArgs& a) {
     else launch_tr<Traits<TASK, NP, STEER_ACC, 1>>(h, a);
 }
 
+#if defined(SG_PART)
+#if SG_PART == 0  // the other families are instantiated by parts 1-4
+extern template void launch_np<TASK_GOAL, 3>(const sg_env*, const LaunchArgs&);
+extern template void launch_np<TASK_GOAL, 4>(const sg_env*, const LaunchArgs&);
+extern template void launch_np<TASK_KEPLER, 1>(const sg_env*, const LaunchArgs&);
+extern template void launch_np<TASK_DNC, 1>(const sg_env*, const LaunchArgs&);
+#elif SG_PART == 1
+template void launch_np<TASK_GOAL, 3>(const sg_env*, const LaunchArgs&);
+#elif SG_PART == 2
+template void launch_np<TASK_GOAL, 4>(const sg_env*, const LaunchArgs&);
+#elif SG_PART == 3
+template void launch_np<TASK_KEPLER, 1>(const sg_env*, const LaunchArgs&);
+#elif SG_PART == 4
+template void launch_np<TASK_DNC, 1>(const sg_env*, const LaunchArgs&);
+#endif
+#endif
+
+#if SG_MAIN_PART
 // enqueue only (no error query: also used inside stream capture)
 static int enqueue(sg_env* h, const LaunchArgs& a) {
 #ifdef SG_DEV_ONLY_GOAL3P  // development builds (seconds instead of minutes): the BASELINE workload's instantiation only
@@ -2214,3 +2249,4 @@ extern "C" int sg_measure_fp64_peak(int device, double ms, double* tflops_out) {
     *tflops_out = best;
     return SG_OK;
 }
+#endif  // SG_MAIN_PART
