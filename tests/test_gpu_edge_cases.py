@@ -156,3 +156,23 @@ def test_checkpoint_round_trip_resumes_bit_identically():
         assert (sa[k] == sb[k]).all() if k != "step_count" else sa[k] == sb[k], k
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("env_id", ["GoalContinuous2P-v0", "GoalContinuous3P-v0", "KeplerEllipseEasy-v0",
+                                    "DoNotCrashContinuous-v0"])
+@pytest.mark.parametrize("n", [1000, 4097])
+def test_float32_observations_every_layout(env_id, n):
+    """obs_dtype=float32 through the split path (K = 1, staged rows + 128-bit warp stores) for every observation
+    width (13, 15, 10, 7) and env counts that end in a partial warp: equals the cast of the float64 rows."""
+    a = sg.make(env_id, n, seed=6, max_episode_steps=25)
+    b = sg.make(env_id, n, seed=6, max_episode_steps=25, obs_dtype="float32")
+    oa, ob = a.reset(), b.reset()
+    assert ob.dtype == torch.float32 and torch.equal(oa.float(), ob)
+    g = torch.Generator(device=a.device).manual_seed(1)
+    for _ in range(40):
+        act = (torch.rand((n, 2), device=a.device, generator=g) * 2 - 1).float()
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act)
+        assert torch.equal(oa.float(), ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    a.close()
+    b.close()
