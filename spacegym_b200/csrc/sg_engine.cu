@@ -1033,13 +1033,16 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
     const uint32_t* q_in = second_queue ? c.q_cont2 : c.q_cont;
     const double* scr_in = second_queue ? c.scr_cont2 : c.scr_cont;
     double st[4] = {0, 0, 0, 0};
+    // The record of a step that hit a terminal event (29 doubles) waits for its queue slot in the thread's own
+    // shared-memory slot, not in registers: the slot comes from a warp-convergent atomic after the loop body.
+    __shared__ __align__(16) EventIO<TR> s_io[kBlock];
     for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
         const uint32_t j = base + threadIdx.x;
         const bool valid = j < count;
         bool is_event = false, need_post = false, reached = false, done = false;
         long long i = 0;
         Integ<TR> S;
-        EventIO<TR> io;
+        EventIO<TR>& io = s_io[threadIdx.x];
         double lx = 0, ly = 0;
         if (valid) {
             i = q_in[j];
