@@ -2,6 +2,12 @@
 // Space-Gym stepping engine.  sm_100a only; no CPU path.
 //
 // Kernels
+//   hot_kernel<TR, OT>     K = 1 (default step path): load, action translate, select_initial_step,
+//                          ONE Runge-Kutta attempt, classify; envs that are done with the step get their
+//                          observation / reward / TimeLimit epilogue here, the others go to device-side queues.
+//   cont_kernel<TR, OT>    queue of envs that need more attempts (25 %): resumes solve_ivp's loop, epilogue.
+//   tail_kernel<TR, OT>    queues of envs with a terminal event (dense output + Brent roots + epilogue) and of
+//                          finished envs that need a new goal or an auto-reset; empties the queues.
 //   step_kernel<TR, OT>    K fused env.step()s per launch, one thread per env: action translate ->
 //                          RK45 with events -> observation -> reward (+ goal resample) -> TimeLimit
 //                          -> auto-reset, state in registers across the K substeps; observation rows
