@@ -210,7 +210,7 @@ def run_b200(args):
     for e in envs:
         e.reset()
         if args.prewarm > 0:
-            e.rollout_random(args.prewarm)  # K fused steps in one launch: steady-state mix of episode ages
+            e.rollout_random(args.prewarm)  # untimed: steady-state mix of episode ages
     L = envs[0]._L
     stream = torch.cuda.current_stream(dev)
     # the env batches are independent: each one is stepped on its own stream, forked from / joined into the
@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prewarm", type=int, default=128, help="untimed env steps per batch (one fused-kernel launch) that bring the envs to their steady-state mix of episode ages before warm-up")
+    ap.add_argument("--prewarm", type=int, default=128, help="untimed env steps per batch that bring the envs to their steady-state mix of episode ages before warm-up")
     ap.add_argument("--batches", type=int, default=None, help="independent env batches in flight (default 16)")
     ap.add_argument("--no-f32", action="store_true", help="skip the float32-observation end-to-end leg")
     ap.add_argument("--env-id", default=None, help="benchmark another registered id (default: the BASELINE workload)")

@@ -50,9 +50,10 @@ extern "C" {
 enum sg_task { SG_TASK_GOAL = 0, SG_TASK_KEPLER = 1, SG_TASK_DONOTCRASH = 2 };
 enum sg_steering { SG_STEER_ACCELERATION = 0, SG_STEER_VELOCITY = 1 }; /* ship_params.py:5-8 */
 enum sg_obs_dtype { SG_OBS_F64 = 0, SG_OBS_F32 = 1 };
-/* How sg_step maps onto kernels.  AUTO: K == 1 runs the split path (hot kernel + continuation and tail
- * kernels fed by device-side work queues, warps stay converged); K > 1 runs the fused kernel (state in
- * registers across the K substeps, rare paths inline). */
+/* How sg_step maps onto kernels.  SPLIT (= AUTO): every env step is a hot kernel + continuation and tail
+ * kernels fed by device-side work queues (warps stay converged); K steps are 3 K launches.  FUSED: one kernel
+ * runs all K substeps with the state in registers and the rare paths inline — one launch, but 3-4 x slower per
+ * env step because every warp pays for every path. */
 enum sg_step_mode { SG_STEP_AUTO = 0, SG_STEP_FUSED = 1, SG_STEP_SPLIT = 2 };
 
 enum sg_status {

@@ -2091,7 +2091,9 @@ extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, do
     if (d_obs && !aligned16(d_obs)) return fail(h, SG_ERR_INVALID, "sg_step: d_obs must be 16-byte aligned");
     if (d_actions && (((uintptr_t)d_actions) & 7u)) return fail(h, SG_ERR_INVALID, "sg_step: d_actions must be 8-byte aligned");
     const int mode = h->cfg.step_mode;
-    const bool split = (mode == SG_STEP_SPLIT) || (mode == SG_STEP_AUTO && K == 1);
+    // auto = split for every K: K split steps (3 K launches) run 3-4 x faster than the register-resident K-fused
+    // kernel (3.3 vs 1.05 G env-steps/s on one 262144-env handle), whose warps pay for every rare path
+    const bool split = (mode == SG_STEP_SPLIT) || (mode == SG_STEP_AUTO);
     LaunchArgs a{};
     a.stream = (cudaStream_t)stream;
     if (!split) {

@@ -154,7 +154,8 @@ class BatchedSpaceEnv:
         return obs, rew[0], done[0], {"TimeLimit.truncated": info["TimeLimit.truncated"][0]}
 
     def step_many(self, actions=None, check_actions=False, K=None, want_obs=True):
-        """K fused steps in one launch. actions: f32 [K, N, 2] (discrete: [..., 0] holds the index) or
+        """K env steps per call (split kernels, or one fused launch with step_mode="fused"). actions: f32 [K, N, 2]
+        (discrete: [..., 0] holds the index) or
         None with K given for synthetic random actions. Returns obs after the last step, reward [K, N],
         done [K, N], info."""
         n = self.num_envs

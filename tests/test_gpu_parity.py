@@ -94,8 +94,8 @@ def test_fused_substeps_and_synthetic_actions(oracle, case):
     n, K, seed = 4096, 12, 99
     cfg = oracle_cfg(oracle, case, max_episode_steps=40)
     env_id, kw = engine_kwargs(case)
-    a = sg.make(env_id, n, seed=seed, max_episode_steps=40, **kw)
-    b = sg.make(env_id, n, seed=seed, max_episode_steps=40, **kw)
+    a = sg.make(env_id, n, seed=seed, max_episode_steps=40, step_mode="fused", **kw)
+    b = sg.make(env_id, n, seed=seed, max_episode_steps=40, step_mode="split", **kw)
     eng = oracle.Engine(cfg, n, seed=seed)
     a.reset(); b.reset(); eng.reset()
     for rep in range(3):
