@@ -745,6 +745,18 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
             active = active_events<TR>(g, gn);
             if (active) {
                 kind = KIND_EVENT;
+                // The 14 stage forces of an event lane wait for their queue slot in the lane's own (otherwise unused)
+                // row of the observation staging area, not in registers across the epilogue of the finished lanes:
+                // 48 bytes of spills -> none at 128 registers (+2 %).  Staging the continuation lanes' integrator
+                // state the same way measured slower.  Needs a 14-double row: f64 observations of Goal 3P / 4P.
+                if (sizeof(OT) == 8 && D >= 14) {
+                    double* r = reinterpret_cast<double*>(sobs) + threadIdx.x * D;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        r[k] = Ax[k];
+                        r[7 + k] = Ay[k];
+                    }
+                }
             } else if (t_new < c.T) {
                 kind = KIND_CONT;
                 S.x = xn; S.y = yn; S.th = thn; S.vx = vxn; S.vy = vyn; S.om = omn;
@@ -813,7 +825,17 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
         save_cont_scene<TR>(c, c.scr_cont, s_cont, e, act);
         if (publish) st_release(c.q_cont + s_cont, (uint32_t)i);  // scratch row visible before "ready"
     }
-    if (kind == KIND_EVENT) save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
+    if (kind == KIND_EVENT) {
+        if (sizeof(OT) == 8 && D >= 14) {
+            const double* r = reinterpret_cast<const double*>(sobs) + threadIdx.x * D;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                Ax[k] = r[k];
+                Ay[k] = r[7 + k];
+            }
+        }
+        save_event<TR>(c, s_event, i, S, h, Ax, Ay, active, lx, ly);
+    }
     if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
     if (obs) {  // rows of queued envs are rewritten by the later kernels
         __syncwarp();
