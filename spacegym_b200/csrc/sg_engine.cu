@@ -1706,12 +1706,16 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     if (h->owns_state) err = cudaMalloc(&h->state, (size_t)h->lay.total_bytes);
     if (err == cudaSuccess) err = cudaMalloc((void**)&h->d_stats, 4 * sizeof(double));
     {   // sub-batches of the split path: multiples of the block size, at least 32768 envs each
-        // Measured on B200 (profiles/r1_notes.md): splitting one handle into concurrent sub-batches does not
-        // pay (2.2 -> 2.3 G env-steps/s at 262144 envs: each sub-batch still walks the same three-kernel
-        // latency chain), while independent handles on their own streams do (3.7 G/s).  Default: one.
-        int want = 1;
+        // Measured on B200 (profiles/r1_notes.md, tools/bench_subbatches.py), one handle stepped back to back:
+        // 262144 envs 3.34 / 3.48 / 3.44 / 3.41 G env-steps/s for 1 / 2 / 3 / 4 concurrent sub-batches (each still
+        // walks the same three-kernel latency chain), 1048576 envs 4.58 / 5.29 / 5.90 / 5.90 G/s (the long thin
+        // tail kernel of one sub-batch hides under the hot kernel of another).  Default: one below 3 x 262144
+        // envs, then one sub-batch per ~350 k envs up to four; SG_SUBBATCHES overrides.
+        int want = n_envs < 786432 ? 1 : (n_envs < 1048576 ? 2 : (n_envs < 2097152 ? 3 : 4));
         const char* env_sub = getenv("SG_SUBBATCHES");
         if (env_sub && atoi(env_sub) > 0) want = atoi(env_sub) > 8 ? 8 : atoi(env_sub);
+        const char* env_timing = getenv("SG_TIMING");
+        if (env_timing && atoi(env_timing)) want = 1;  // the per-kernel timing aid synchronises inside the step
         h->n_sub = want;
         const char* env_graph = getenv("SG_GRAPHS");
         h->use_graphs = env_graph ? atoi(env_graph) : 1;
