@@ -103,3 +103,22 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"import\s+oracle|from\s+oracle|sg_oracle|so_engine|so_step", text), f
+
+
+def test_bind_host_to_gpu_is_safe_without_a_gpu():
+    """The NUMA helper never raises and never leaves the process with an empty CPU set."""
+    before = os.sched_getaffinity(0)
+    try:
+        cpus = sg.bind_host_to_gpu(0)
+        assert len(cpus) >= 1 and cpus <= before
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_build_script_knows_every_part():
+    """spacegym_b200/build.py compiles SG_PART=0..N_PARTS-1; the source must give every part an instantiation."""
+    from spacegym_b200 import build
+    src = open(os.path.join(ROOT, "spacegym_b200", "csrc", "sg_engine.cu")).read()
+    for k in range(1, build.N_PARTS):
+        assert re.search(rf"#elif SG_PART == {k}\ntemplate void launch_np<", src), k
+    assert f"#elif SG_PART == {build.N_PARTS}" not in src
