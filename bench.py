@@ -50,6 +50,11 @@ METRIC = "env-steps/sec (batched, device-timed)"
 UNIT = "env-steps/s"
 
 
+def workload_name(n):
+    """The workload both arms are quoted on (BASELINE.json configs[2])."""
+    return f"{ENV_ID} {n} envs/step/GPU auto-reset hexagonal-tiling TimeLimit500 random f32 actions, K=1"
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,7 +168,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{ENV_ID} {n} envs/step auto-reset TimeLimit500 random actions (CPU oracle port)"},
+        "config": {"workload": workload_name(ENVS_PER_STEP),
+                   "step_path": "CPU oracle port (oracle/sg_oracle.c), OpenMP over envs",
+                   "envs_per_step_sampled": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -387,8 +394,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{ENV_ID} {n} envs/step/GPU auto-reset hexagonal-tiling TimeLimit500 "
-                                   f"random f32 actions, K=1 (one sg_step call per step: hot/continuation/tail kernels)",
+            "config": {"workload": workload_name(n),
+                       "step_path": "one sg_step call per step: hot / continuation / tail kernels",
                        "envs_per_gpu_per_step": n, "total_envs_per_step": total,
                        "l2": f"inputs larger than L2: {N_BATCHES} env batches stepped round-robin "
                              f"({N_BATCHES * n * (ALGO_BYTES_PER_STEP + 60) / 1e6:.0f} MB working set)",
