@@ -96,8 +96,12 @@ __device__ __forceinline__ double inv_tenth_root(double x) { return pow(x, -0.1)
 #endif
 // 0.9 * err^(-1/5) of the step-size controller, from err2 = err^2, clamped to the range in which the
 // caller's min(10, .) / max(0.2, .) can still depend on the value (outside it the clamp decides)
+// A NaN error norm (non-finite state) must take the upper clamp: the factor is then below 0.2, the rejected step
+// shrinks by max(0.2, .) = 0.2 as it does in SciPy (where the comparison with NaN fails), and the attempt loop
+// ends at min_step with "step size too small" instead of never ending.
 __device__ __forceinline__ double controller_factor(double err2) {
-    return 0.9 * inv_tenth_root(fmin(fmax(err2, 1e-14), 1e10));
+    const double e = (err2 <= 1e10) ? fmax(err2, 1e-14) : 1e10;
+    return 0.9 * inv_tenth_root(e);
 }
 
 enum { TASK_GOAL = 0, TASK_KEPLER = 1, TASK_DNC = 2 };  // DNC: do_not_crash.py (Kepler-like scene, no orbit)

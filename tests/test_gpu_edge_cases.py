@@ -176,3 +176,33 @@ def test_float32_observations_every_layout(env_id, n):
         assert torch.equal(oa.float(), ob) and torch.equal(ra, rb) and torch.equal(da, db)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("mode", ["split", "fused"])
+def test_non_finite_state_terminates_and_is_flagged(mode):
+    """A NaN / Inf state injected through set_state must not hang the integrator loops: the env is flagged
+    (status bits: step too small / non-finite) like the reference's `assert ode_solution.success`
+    (dynamic_model.py:120), and every other env of the batch steps on unharmed."""
+    n = 512
+    env = sg.make("GoalContinuous3P-v0", n, seed=3, step_mode=mode, auto_reset=0, max_episode_steps=0)
+    ref = sg.make("GoalContinuous3P-v0", n, seed=3, step_mode=mode, auto_reset=0, max_episode_steps=0)
+    env.reset()
+    ref.reset()
+    st = env.get_state()
+    ship = st["ship"].clone()
+    ship[5, 0] = float("nan")      # x
+    ship[77, 3] = float("inf")     # vx
+    ship[300, 2] = float("nan")    # heading
+    env.set_state({"ship": ship})
+    act = torch.zeros((n, 2), dtype=torch.float32, device=env.device)
+    for _ in range(3):
+        o, r, d, _ = env.step(act)
+        o2, r2, d2, _ = ref.step(act)
+    torch.cuda.synchronize()
+    status = env.get_state()["status"].cpu().numpy()
+    bad = np.zeros(n, dtype=bool)
+    bad[[5, 77, 300]] = True
+    assert (status[bad] != 0).all() and (status[~bad] == 0).all()
+    assert torch.equal(o[~torch.as_tensor(bad, device=o.device)], o2[~torch.as_tensor(bad, device=o.device)])
+    env.close()
+    ref.close()
