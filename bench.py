@@ -204,9 +204,9 @@ def run_b200(args):
     n = args.envs
     total = n * world
     # envs sharded by contiguous global index range, no data-path collective
-    envs = [sg.make(ENV_ID, n, device=dev, seed=1000 + b, first_env_index=rank * n, **ENV_KW) for b in range(N_BATCHES)]
+    envs = [sg.make(ENV_ID, n, device=dev, seed=1000 + 100000 * args.seed + b, first_env_index=rank * n, **ENV_KW) for b in range(N_BATCHES)]
     gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    gen.manual_seed(1234 + 100000 * args.seed + rank)
     actions = [[(torch.rand((1, n, 2), device=dev, generator=gen) * 2 - 1).float().contiguous()
                 for _ in range(ACTION_SETS)] for _ in range(N_BATCHES)]
     D = envs[0].obs_dim
@@ -396,7 +396,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n),
                        "step_path": "one sg_step call per step: hot / continuation / tail kernels",
-                       "envs_per_gpu_per_step": n, "total_envs_per_step": total,
+                       "envs_per_gpu_per_step": n, "total_envs_per_step": total, "seed": args.seed,
                        "l2": f"inputs larger than L2: {N_BATCHES} env batches stepped round-robin "
                              f"({N_BATCHES * n * (ALGO_BYTES_PER_STEP + 60) / 1e6:.0f} MB working set)",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
@@ -452,6 +452,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seed", type=int, default=0, help="offsets the env and action seeds of the timed batches (SURVEY 8d: seeds 0, 1, 2, median)")
     ap.add_argument("--envs", type=int, default=ENVS_PER_STEP, help="envs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm", type=int, default=128, help="untimed env steps per batch that bring the envs to their steady-state mix of episode ages before warm-up")
