@@ -368,6 +368,17 @@ def run_b200(args):
             e.close()
 
     stats = envs[0].stats(allreduce=world > 1)  # the engine's only collective: episode statistics
+    # integrity of what was just timed (outside the timed region): sticky per-env fault bits (step too small, lost
+    # Brent bracket, free-list overflow, non-finite state) and non-finite ship states over every batch of this rank
+    torch.cuda.synchronize(dev)
+    faults = torch.zeros(2, dtype=torch.int64, device=dev)
+    for e in envs:
+        v = e.state_views()
+        faults[0] += (v["status"] != 0).sum()
+        faults[1] += (~torch.isfinite(v["ship"])).any(dim=0).sum()
+    if world > 1:
+        dist.all_reduce(faults)
+    faults = [int(x) for x in faults.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src = read_peaks()
@@ -423,6 +434,8 @@ def run_b200(args):
             "host_cpus_rank0": len(cpus),
             "clocks": clocks,
             "episode_stats": stats,
+            "integrity": {"envs_with_fault_bits": faults[0], "envs_with_non_finite_state": faults[1],
+                          "envs_checked": total * N_BATCHES, "when": "after the timed region"},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
