@@ -279,6 +279,34 @@ def run_b200(args):
     ms = float(t.item())
     value = total * args.steps / (ms * 1e-3)
 
+    # ---- one vector env alone: a single handle stepped back to back on one stream (what a user with ONE
+    # BatchedSpaceEnv of this size gets; its state and outputs fit the L2, so this is the warm-L2 figure) ----
+    single = None
+    if rank == 0:
+        e0, o0 = envs[0], outs[0]
+        s_steps = max(50, min(args.steps, 400))
+
+        def single_step(k):
+            a = actions[0][k % ACTION_SETS]
+            rc = L.sg_step(e0._h, a.data_ptr(), 1, o0["obs"].data_ptr(), o0["rew"].data_ptr(), o0["done"].data_ptr(),
+                           o0["trunc"].data_ptr(), stream.cuda_stream)
+            if rc != 0:
+                raise RuntimeError(L.sg_last_error(e0._h))
+        for k in range(10):
+            single_step(k)
+        torch.cuda.synchronize(dev)
+        sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sv0.record(stream)
+        for k in range(s_steps):
+            single_step(k)
+        sv1.record(stream)
+        torch.cuda.synchronize(dev)
+        s_ms = sv0.elapsed_time(sv1)
+        single = {"value": n * s_steps / (s_ms * 1e-3), "unit": UNIT, "envs": n, "batches": 1, "steps": s_steps,
+                  "us_per_step": s_ms * 1e3 / s_steps,
+                  "how": "one handle, sg_step back to back on one stream, CUDA events, warm L2"}
+    barrier()
+
     # ---- end to end: public API with host buffers (pinned), copies inside the timed region ----
     # gym.vector step_async / step_wait over the same env batches: every step uploads its actions
     # from host memory and downloads observation, reward, done and truncated into host memory.
@@ -427,6 +455,7 @@ def run_b200(args):
                                              "frac": (fp64_ach / fp64_peak) if fp64_peak else None},
                                     "note": "all kernels of a step (hot+continuation+tail), from `value`"},
             "kernel_times": kt,
+            "single_handle": single,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "BatchedSpaceEnv.step_async(numpy)/step_wait() -> sg_step_host_async/sg_host_wait, all env batches in flight"},
             "e2e_f32obs": e2e32,

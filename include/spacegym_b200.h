@@ -12,7 +12,7 @@
  *   sg_create / sg_destroy                   SpaceshipEnv.__post_init__ spaceship_env.py:50-57 (+ env.seed :92-94)
  *   sg_reset / sg_reset_host                 SpaceshipEnv.reset spaceship_env.py:59-66 -> GoalEnv._reset goal.py:133-145
  *                                            / KeplerEnv._reset kepler.py:233-267
- *   sg_step / sg_step_host                   SpaceshipEnv.step spaceship_env.py:68-78 -> ShipState.step
+ *   sg_step / sg_step_host[_block_async]     SpaceshipEnv.step spaceship_env.py:68-78 -> ShipState.step
  *                                            dynamic_model.py:42-57,94-125 (scipy solve_ivp RK45 + events),
  *                                            _make_observation :113-131, GoalEnv._reward goal.py:147-158,
  *                                            KeplerEnv._reward kepler.py:111-156; gym TimeLimit + vector
@@ -116,6 +116,17 @@ typedef struct sg_layout {
     int64_t status;     /* u32 [N]: sticky SG_ENV_* bits */
 } sg_layout;
 
+/* Byte offsets inside the per-step HOST result block of sg_step_host_block_async: one contiguous block, so a step
+ * is one device->host copy.  flags: bit 0 = done, bit 1 = truncated (TimeLimit; implies done). */
+typedef struct sg_host_layout {
+    int64_t n_envs;
+    int64_t total_bytes;
+    int64_t obs;     /* obs_dtype [N][D] (absent when want_obs = 0: obs == reward) */
+    int64_t reward;  /* f64 [N] */
+    int64_t flags;   /* u8 [N] */
+    int32_t obs_dtype, obs_dim;
+} sg_host_layout;
+
 typedef struct sg_env sg_env; /* opaque handle */
 
 /* ---- configuration ------------------------------------------------------------ */
@@ -140,7 +151,7 @@ void* sg_state_ptr(const sg_env* env);
 /* Reset envs whose d_mask byte is non-zero (NULL: all).  d_obs: [N][D] or NULL. */
 int sg_reset(sg_env* env, const uint8_t* d_mask, void* d_obs, void* stream);
 
-/* K fused env steps per launch.
+/* K env steps (step_mode AUTO / SPLIT: 3 K kernel launches; FUSED: one launch).
  *   d_actions  f32 [K][N][2] (continuous: raw Box(-1,1) action; discrete: [..][0] = index 0..5),
  *              or NULL: synthetic uniform-random actions from the engine's counter RNG.
  *   d_obs      [N][D] observation after the last step (reset observation where the env
@@ -159,6 +170,16 @@ int sg_step_host(sg_env* env, const float* h_actions, int K, void* h_obs, double
 int sg_step_host_async(sg_env* env, const float* h_actions, int K, void* h_obs, double* h_reward,
                        uint8_t* h_done, uint8_t* h_truncated);
 int sg_host_wait(sg_env* env);
+/* Packed form of the same call (what BatchedSpaceEnv.step(numpy) uses): ONE host->device copy of the actions
+ * f32 [N][2] (NULL: synthetic actions), one env step, ONE device->host copy of a contiguous result block laid out
+ * by sg_host_block_layout.  obs_dtype is chosen per call (float32 — the dtype observation_space declares,
+ * spaceship_env.py:110-111 — halves the block); want_obs = 0 leaves the observation on the device.  The work is
+ * enqueued on the handle's own stream, ordered after everything already enqueued on `after_stream` (the stream the
+ * caller uses for sg_reset / sg_step / state writes on this handle; NULL = legacy default stream).  Pinned host
+ * memory keeps the copies asynchronous.  sg_host_wait() blocks until the block holds the results. */
+int sg_host_block_layout(const sg_env* env, int obs_dtype, int want_obs, sg_host_layout* out);
+int sg_step_host_block_async(sg_env* env, const float* h_actions, void* h_block, int obs_dtype, int want_obs,
+                             void* after_stream);
 
 /* RHS of the ship ODE for every env at its current state: d_out f64 [N][6]. */
 int sg_vector_field(sg_env* env, const float* d_actions, double* d_out, void* stream);
@@ -170,6 +191,9 @@ int sg_stats(sg_env* env, double out[4], void* stream);
 int sg_stats_reset(sg_env* env, void* stream);
 uint64_t sg_step_count(const sg_env* env);           /* env steps taken per env (drives the action RNG) */
 int sg_set_step_count(sg_env* env, uint64_t steps);
+/* env.seed(seed) (spaceship_env.py:92-94, goal.py:74-77): re-key every env's random streams and restart their
+ * counters (and the step counter); the next reset / step draws from the new streams.  Synchronises the device. */
+int sg_reseed(sg_env* env, uint64_t seed);
 int64_t sg_kernel_launches(const sg_env* env);       /* kernels launched by this handle */
 /* Measurement aid, active when the handle was created with SG_TIMING=1 in the environment (sg_step then
  * synchronises inside every step): out[0..2] = mean milliseconds of the {hot, continuation, tail} kernels per

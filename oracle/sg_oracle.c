@@ -1015,13 +1015,19 @@ void so_engine_step(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed
             so_draws_philox(&d, seed, gidx, e->rng_ctr);
             double r;
             int32_t reached = 0;
-            int dn = so_step(cfg, e, a, &d, o, &r, &reached, NULL);
+            /* the goal resample of goal.py:155-157 is drawn below, not inside so_step: see the comment there */
+            int dn = so_step(cfg, e, a, NULL, o, &r, &reached, NULL);
             e->elapsed += 1;
             int trunc = 0;
             if (e->elapsed >= cfg->max_episode_steps) { /* gym TimeLimit (0.21) */
                 trunc = !dn;
                 dn = 1;
             }
+            /* Engine convention (the engine's streams are its own, SURVEY Appendix C: only the mapping from draws
+             * to states is the reference's): an env that reaches its goal and restarts in the same step draws no
+             * new goal -- the reset that follows overwrites goal and tiling -- so a reset always starts at the
+             * env's current Philox block, whatever happened in the step. */
+            if (reached && !(dn && auto_reset)) so_find_new_goal(cfg, e, &d);
             e->ep_return += r;
             s3 += reached;
             if (dn) {

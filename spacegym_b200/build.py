@@ -15,7 +15,7 @@ import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("sg_engine.cu", "sg_device.cuh")] + [
+SRC = [os.path.join(HERE, "csrc", f) for f in ("sg_engine.cu", "sg_device.cuh", "sg_tail.cuh")] + [
     os.path.join(ROOT, "include", "spacegym_b200.h")]
 OUT = os.path.join(HERE, "libspacegym_b200.so")
 N_PARTS = 5

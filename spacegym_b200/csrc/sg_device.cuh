@@ -179,6 +179,7 @@ struct DevCfg {
     long long first_env;
     unsigned long long seed;
     int max_episode_steps, randomize, auto_reset, rows, cols;
+    int pack_flags;  // 1: done_out holds done | truncated << 1 in one byte per env (host result block), trunc_out unused
     // physics
     double T, half_ws, two_over_ws, om_max, inv_mass, moi;
     double max_engine, max_thruster;          // float64 action path (discrete)

@@ -25,6 +25,7 @@
 
 #include "../../include/spacegym_b200.h"
 #include "sg_device.cuh"
+#include "sg_tail.cuh"
 
 // SG_PART: the library can be built as five translation units compiled in parallel (spacegym_b200/build.py):
 // part 0 = C ABI + dispatch + the 2-planet GoalEnv kernels, parts 1-4 = the kernels of one more env family each
@@ -260,6 +261,9 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
             if (TR::TASK == TASK_GOAL && reached) {
                 r += c.sparse;
                 st_goal += 1;
+            }
+            // the new goal of an env that restarts in the same step would be overwritten by the reset: not drawn
+            if (TR::TASK == TASK_GOAL && reached && !(dn && c.auto_reset)) {
                 double gxy[2];
                 rng.fresh_block();
                 resample_goal<TR>(c, i, &rng, gxy, &status);
@@ -284,7 +288,7 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
                 }
             }
             if (reward) reward[(long long)k * c.stride + i] = r;
-            if (done_out) done_out[(long long)k * c.stride + i] = dn ? 1 : 0;
+            if (done_out) done_out[(long long)k * c.stride + i] = (uint8_t)((dn ? 1 : 0) | ((c.pack_flags && trunc) ? 2 : 0));
             if (trunc_out) trunc_out[(long long)k * c.stride + i] = trunc ? 1 : 0;
         }
         store_ship<TR>(c, i, e);
@@ -417,6 +421,19 @@ __device__ __forceinline__ void block_stats_flush(const DevCfg& c, double (&st)[
     }
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// The kernels of a step (and of consecutive steps) form a chain on one stream.  Launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, a kernel's CTAs may become resident while the previous kernel
+// drains; pdl_wait() (griddepcontrol.wait) then blocks until the previous grid has completed and its writes are
+// visible.  Everything a kernel reads that an earlier kernel of the chain wrote comes after pdl_wait().
+// pdl_trigger() (griddepcontrol.launch_dependents) is issued once a CTA has no long work left.  Without the launch
+// attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 template <class TR>
 __device__ __forceinline__ Act fetch_action(const DevCfg& c, const float* __restrict__ actions, long long i,
                                             unsigned long long step0) {
@@ -471,7 +488,7 @@ __device__ __forceinline__ void finish_env(const DevCfg& c, long long i, EnvRegs
     c.elapsed[i] = elapsed;
     c.ep_return[i] = ep_ret;
     if (reward) reward[i] = r;
-    if (done_out) done_out[i] = dn ? 1 : 0;
+    if (done_out) done_out[i] = (uint8_t)((dn ? 1 : 0) | ((c.pack_flags && trunc) ? 2 : 0));
     if (trunc_out) trunc_out[i] = trunc ? 1 : 0;
     done = dn;
 }
@@ -483,7 +500,7 @@ __device__ __forceinline__ void post_env(const DevCfg& c, long long i, bool reac
     Rng rng;
     rng.open(c.seed, (unsigned long long)(c.first_env + i), c.rng_ctr[i]);
     uint32_t status = 0;
-    if (TR::TASK == TASK_GOAL && reached) {
+    if (TR::TASK == TASK_GOAL && reached && !(done && c.auto_reset)) {
         double gxy[2];
         rng.fresh_block();
         resample_goal<TR>(c, i, &rng, gxy, &status);
@@ -772,6 +789,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
             }
         }
     }
+    if (!STAGED && !publish) pdl_trigger();  // the long part of this CTA is over: the next kernel of the chain may launch
     // queue appends at warp-converged points.  The continuation / event atomics are issued BEFORE the
     // epilogue of the finished lanes, whose arithmetic then covers the L2 round trip of the atomics.
     const bool is_cont = kind == KIND_CONT || kind == KIND_CONT_REJECTED;
@@ -847,9 +865,10 @@ template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
 hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
-    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     __shared__ __align__(16) OT sobs[kBlock * TR::D];
     __shared__ double stash[4 * kBlock];
+    pdl_wait();  // the previous step's tail kernel has written the state and emptied the queues
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     double st[4] = {0, 0, 0, 0};
     hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)blockIdx.x * kBlock, sobs, st, false,
                       nullptr, stash);
@@ -1057,15 +1076,26 @@ template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock, SG_CONT_MINB)
 cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out, int second_queue) {
+    // The record of a step that hit a terminal event (29 doubles) waits for its queue slot in the thread's own
+    // shared-memory slot, not in registers: the slot comes from a warp-convergent atomic after the loop body.
+    __shared__ __align__(16) EventIO<TR> s_io[kBlock];
+    pdl_wait();
     const uint32_t count = second_queue ? c.q_counts[6] : c.q_counts[0];
     const uint32_t* q_in = second_queue ? c.q_cont2 : c.q_cont;
     const double* scr_in = second_queue ? c.scr_cont2 : c.scr_cont;
     double st[4] = {0, 0, 0, 0};
-    // The record of a step that hit a terminal event (29 doubles) waits for its queue slot in the thread's own
-    // shared-memory slot, not in registers: the slot comes from a warp-convergent atomic after the loop body.
-    __shared__ __align__(16) EventIO<TR> s_io[kBlock];
-    for (uint32_t base = blockIdx.x * kBlock; base < count; base += gridDim.x * kBlock) {
-        const uint32_t j = base + threadIdx.x;
+    // Work is handed out per WARP from a ticket counter: the entries of a warp take as long as its slowest lane (one
+    // to four more Runge-Kutta steps), so a static split leaves the grid waiting for its unluckiest CTA.  The first
+    // round needs no ticket (warp w of the grid takes chunk w).
+    const uint32_t warps_in_grid = gridDim.x * (kBlock / 32);
+    uint32_t chunk = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    for (; (unsigned long long)chunk * 32 < count;) {
+        const uint32_t j = chunk * 32 + (threadIdx.x & 31);
+        {
+            uint32_t t = 0;
+            if ((threadIdx.x & 31) == 0) t = atomicAdd(&c.q_counts[10], 1u);
+            chunk = warps_in_grid + __shfl_sync(0xffffffffu, t, 0);
+        }
         const bool valid = j < count;
         bool is_event = false, need_post = false, reached = false, done = false;
         long long i = 0;
@@ -1112,6 +1142,7 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         }
         if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
     }
+    pdl_trigger();
     warp_stats_flush(c, st);  // no block barrier: a warp leaves as soon as its own entries are done
 }
 
@@ -1124,6 +1155,7 @@ template <class TR, typename OT>
 __global__ void __launch_bounds__(kTailBlock)
 tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    pdl_wait();
     const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     const uint32_t n_event = c.q_counts[1], n_post = c.q_counts[2];
     const uint32_t total = n_event + n_post;
@@ -1213,7 +1245,203 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
     if (last) {  // ... and advances the device-side step counter that keys the synthetic-action stream
         if (threadIdx.x < 4) c.q_counts[threadIdx.x] = 0;
         if (threadIdx.x == 5) c.q_counts[6] = 0;
-        if (threadIdx.x >= 7 && threadIdx.x <= 9) c.q_counts[threadIdx.x] = 0;
+        if (threadIdx.x >= 7 && threadIdx.x <= 10) c.q_counts[threadIdx.x] = 0;
+        if (threadIdx.x == 4) *reinterpret_cast<unsigned long long*>(c.q_counts + 4) = step0 + 1;
+    }
+}
+
+
+// =================================================================================================================
+// Tail kernel, second form: latency first.  CTA = two warps working on the SAME 32 queue entries:
+//   warp 0 ("E"): terminal events — dense output, roots, terminal state, reward / done / statistics;
+//   warp 1 ("R"): whatever needs the env's random stream — the auto-reset of those envs (every event is terminal, so
+//                 `done` is known before the root is), and for the post-queue entries the goal resample / reset.
+// The two are independent: the reset state does not depend on where the episode ended, and an env that restarts in
+// the same step draws no new goal (it would be overwritten).  The only hazard is that R overwrites scene fields E
+// still has to read; E signals "my loads are done" on a named barrier (bar.arrive, non-blocking) and R waits on it
+// before its stores.  The critical path of the kernel is max(E, R) instead of E + R.
+// =================================================================================================================
+constexpr int kTail2Block = 64;
+#ifndef SG_TAIL2_MINB
+#define SG_TAIL2_MINB 4
+#endif
+template <class TR, typename OT>
+__global__ void __launch_bounds__(kTail2Block, SG_TAIL2_MINB)
+tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
+             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
+    __shared__ double s_u[2 * kDrawBlocks * 32];  // R: the lanes' precomputed uniforms, element k of lane l at [k * 32 + l]
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_wait();
+    const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
+    const uint32_t n_event = c.q_counts[1], n_post = c.q_counts[2];
+    const uint32_t total = n_event + n_post;
+    const long long cap = c.q_cap;
+    double st[4] = {0, 0, 0, 0};
+    for (uint32_t base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+        const uint32_t j = base + lane;
+        if (role == 0) {
+            // ---------------- E: terminal events ----------------
+            const bool mine = j < n_event;
+            long long i = 0;
+            EnvRegs<TR> e;
+            DenseQ<TR> d;
+            double Ax[7], Ay[7], lx = 0, ly = 0, ep_ret0 = 0;
+            uint32_t active = 0, elapsed0 = 0;
+            Act act;
+            if (mine) {
+                const double* p = c.scr_event + j;
+                i = c.q_event[j];
+                d.x0 = p[0 * cap]; d.y0 = p[1 * cap]; d.th0 = p[2 * cap]; d.vx0 = p[3 * cap]; d.vy0 = p[4 * cap];
+                d.om0 = p[5 * cap]; d.h = p[6 * cap]; d.t_old = p[7 * cap];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    Ax[k] = p[(8 + k) * cap];
+                    Ay[k] = p[(15 + k) * cap];
+                }
+                lx = p[22 * cap]; ly = p[23 * cap];
+                active = (uint32_t)p[24 * cap];
+                load_env<TR>(c, i, e);
+                act = fetch_action<TR>(c, actions, i, step0);
+                elapsed0 = c.elapsed[i];
+                ep_ret0 = c.ep_return[i];
+            }
+            bar_arrive(1, kTail2Block);  // every read of the old scene is done: R may overwrite it
+            if (mine) {
+                d.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
+                dense_build<TR>(d, Ax, Ay);
+                uint32_t status = 0;
+                double x, y, th, vx, vy, om;
+                terminal_state<TR>(c, d, e.px, e.py, active, x, y, th, vx, vy, om, status);
+                commit_state<TR>(e, x, y, th, vx, vy, om, status);
+                double gd[TR::NEV], pd[TR::NP], ipd[TR::NP];
+                event_values_inv<TR>(c, e, e.x, e.y, e.om, gd, pd, ipd);
+                const bool want_row = obs && !c.auto_reset;  // with auto-reset the reset observation replaces it
+                double sn = 0, cs = 1;
+                if (want_row) sincos_cold(e.th, &sn, &cs);
+                OT row[TR::D];
+                // finish_env without the state stores an auto-reset would overwrite anyway
+                if (want_row) make_obs_inv<TR, OT>(c, e, cs, sn, ipd, row);
+                double r;
+                bool reached = false;
+                if (TR::TASK == TASK_GOAL) {
+                    double cur;
+                    r = goal_reward<TR>(c, e, lx, ly, pd, cur);
+                    reached = cur < c.goal_radius;
+                    if (reached) {
+                        r += c.sparse;
+                        st[3] += 1;
+                    }
+                } else if (TR::TASK == TASK_KEPLER) {
+                    r = kepler_reward<TR>(c, e, act);
+                } else {
+                    r = c.const_reward;
+                }
+                const uint32_t elapsed = elapsed0 + 1;
+                const double ep_ret = ep_ret0 + r;
+                st[0] += ep_ret;  // every event is terminal: the episode ends here (TimeLimit cannot truncate it)
+                st[1] += (double)elapsed;
+                st[2] += 1;
+                if (reward) reward[i] = r;
+                if (done_out) done_out[i] = 1;
+                if (trunc_out) trunc_out[i] = 0;
+                if (!c.auto_reset) {
+                    store_ship<TR>(c, i, e);
+                    c.elapsed[i] = elapsed;
+                    c.ep_return[i] = ep_ret;
+                    if (want_row) {
+#pragma unroll
+                        for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
+                    }
+                    if (TR::TASK == TASK_GOAL && reached) {  // rare configuration: the serial draw session
+                        Rng rng;
+                        rng.open(c.seed, (unsigned long long)(c.first_env + i), c.rng_ctr[i]);
+                        double gxy[2];
+                        resample_goal<TR>(c, i, &rng, gxy, &status);
+                        c.goal[i] = gxy[0];
+                        c.goal[c.stride + i] = gxy[1];
+                        c.rng_ctr[i] = rng.ctr;
+                    }
+                }
+                if (status) atomicOr(&c.status[i], status);
+            }
+        } else {
+            // ---------------- R: resets and goal resamples ----------------
+            long long i = 0;
+            bool do_reset = false, do_goal = false;
+            if (j < n_event) {
+                i = c.q_event[j];
+                do_reset = c.auto_reset != 0;
+            } else if (j < total) {
+                const uint32_t w = c.q_post[j - n_event];
+                i = (long long)(w & kPostIndex);
+                const bool reached = (w & kPostReached) != 0, done = (w & kPostDone) != 0;
+                do_reset = done && c.auto_reset;
+                do_goal = TR::TASK == TASK_GOAL && reached && !do_reset;
+            }
+            const bool work = do_reset || do_goal;
+            uint32_t ctr = 0;
+            Tiles t;
+            if (work) {
+                ctr = c.rng_ctr[i];
+                if (do_goal) load_tiles(c, i, t);
+            }
+            if (__any_sync(0xffffffffu, work)) {
+                if (work) philox_fill<draw_blocks<TR>()>(c.seed, (unsigned long long)(c.first_env + i), ctr, s_u + lane);
+            }
+            Draws rng;
+            rng.open(s_u + lane);
+            uint32_t status = 0;
+            double out[8 + 2 * TR::NP];
+            double gx = 0, gy = 0;
+            if (do_reset) reset_env_t<TR>(c, rng, out, t, status);
+            if (do_goal) find_new_goal_t<TR::NP>(c, t, rng, gx, gy, status);
+            bar_sync(1, kTail2Block);  // E has read what it needs of these envs
+            if (do_reset) {
+                EnvRegs<TR> e;
+                e.ecc = e.ang = 0.0;
+                if (TR::TASK == TASK_KEPLER && !c.randomize) {  // the reference orbit stays
+                    e.ecc = c.orbit[i];
+                    e.ang = c.orbit[c.stride + i];
+                }
+                e.px[0] = e.py[0] = 0.0;
+                e.gx = e.gy = 0.0;
+                adopt_reset<TR>(c, e, out);
+                store_ship<TR>(c, i, e);
+                if (TR::TASK == TASK_GOAL || (TR::TASK == TASK_KEPLER && c.randomize)) store_scene<TR>(c, i, e, true);
+                if (TR::TASK == TASK_GOAL) store_tiles(c, i, t, true);
+                c.elapsed[i] = 0;
+                c.ep_return[i] = 0.0;
+                if (obs) {
+                    double sn, cs;
+                    sincos_2pi(e.th, sn, cs);
+                    OT row[TR::D];
+                    make_obs_cs<TR, OT>(c, e, cs, sn, row);
+#pragma unroll
+                    for (int k = 0; k < TR::D; ++k) obs[i * TR::D + k] = row[k];
+                }
+            }
+            if (do_goal) {
+                c.goal[i] = gx;
+                c.goal[c.stride + i] = gy;
+                store_tiles(c, i, t, false);
+            }
+            if (work) c.rng_ctr[i] = ctr + rng.blocks_used();
+            if (status) atomicOr(&c.status[i], status);
+        }
+        __syncthreads();  // one barrier phase per sweep: E may not run ahead into the next sweep's arrive
+    }
+    pdl_trigger();
+    warp_stats_flush(c, st);
+    // the last block to finish empties the queues for the next step
+    __shared__ bool last;
+    __syncthreads();
+    __threadfence();
+    if (threadIdx.x == 0) last = (atomicAdd(&c.q_counts[3], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {  // ... and advances the device-side step counter that keys the synthetic-action stream
+        if (threadIdx.x < 4) c.q_counts[threadIdx.x] = 0;
+        if (threadIdx.x == 5) c.q_counts[6] = 0;
+        if (threadIdx.x >= 7 && threadIdx.x <= 10) c.q_counts[threadIdx.x] = 0;
         if (threadIdx.x == 4) *reinterpret_cast<unsigned long long*>(c.q_counts + 4) = step0 + 1;
     }
 }
@@ -1228,24 +1456,31 @@ template <class TR, typename OT>
 __global__ void __launch_bounds__(kBlock)
 reset_kernel(const DevCfg c, const uint8_t* __restrict__ mask, OT* __restrict__ obs) {
     constexpr int D = TR::D;
+    __shared__ double s_u[2 * kDrawBlocks * kBlock];  // per warp: 32 lanes x 32 draws, element k of lane l at [k * 32 + l]
     const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (i >= c.n) return;
-    if (mask && !mask[i]) return;
     EnvRegs<TR> e;
     load_env<TR>(c, i, e);
-    Rng rng;
-    rng.open(c.seed, (unsigned long long)(c.first_env + i), c.rng_ctr[i]);
-    uint32_t status = 0;
-    double out[8 + 2 * TR::NP];
-    reset_env<TR>(c, i, &rng, out, &status);
-    adopt_reset<TR>(c, e, out);
-    store_ship<TR>(c, i, e);
-    store_scene<TR>(c, i, e, true);
-    c.elapsed[i] = 0;
-    c.ep_return[i] = 0.0;
-    c.rng_ctr[i] = rng.ctr;
-    if (status) c.status[i] |= status;
-    if (obs) {
+    if (!mask || mask[i]) {
+        double* u = s_u + (threadIdx.x >> 5) * (2 * kDrawBlocks * 32) + (threadIdx.x & 31);
+        const uint32_t ctr = c.rng_ctr[i];
+        philox_fill<draw_blocks<TR>()>(c.seed, (unsigned long long)(c.first_env + i), ctr, u);
+        Draws rng;
+        rng.open(u);
+        uint32_t status = 0;
+        double out[8 + 2 * TR::NP];
+        Tiles t;
+        reset_env_t<TR>(c, rng, out, t, status);
+        adopt_reset<TR>(c, e, out);
+        store_ship<TR>(c, i, e);
+        store_scene<TR>(c, i, e, true);
+        if (TR::TASK == TASK_GOAL) store_tiles(c, i, t, true);
+        c.elapsed[i] = 0;
+        c.ep_return[i] = 0.0;
+        c.rng_ctr[i] = ctr + rng.blocks_used();
+        if (status) c.status[i] |= status;
+    }
+    if (obs) {  // envs outside the mask report their current observation
         OT row[D];
         make_obs<TR, OT>(c, e, row);
 #pragma unroll
@@ -1337,17 +1572,20 @@ struct sg_env {
     cudaStream_t hi_stream;
     cudaEvent_t ev_hot, ev_tail;
     int use_priority, use_fused, use_cont1, use_staged;
+    int use_pdl;      // SG_PDL (default 1): programmatic dependent launch along the kernel chain
+    int tail_mode;    // SG_TAIL: 2 (default) = two-role latency-first tail kernel, 1 = the serial round-1 form
+    int tail_grid;    // SG_TAIL_CTAS: CTAs per SM of the tail kernel's grid (32 queue entries per CTA and sweep)
     int timing;                 // SG_TIMING=1: CUDA events around every kernel of the split path
     cudaEvent_t tev[5];
     double t_acc[4];
     double q_acc[3];            // mean entries of the continuation / event / post queues
     long long t_n;
     struct GraphEntry {
-        const void* key[5];
+        const void* key[6];
         cudaGraphExec_t exec;
         uint64_t stamp;
     } graphs[16];
-    int n_graphs;
+    int n_graphs, graph_misses;
     uint64_t graph_clock;
     int use_graphs;
     uint64_t step_count;
@@ -1355,9 +1593,11 @@ struct sg_env {
     std::string err;
     // staging for the *_host entry points
     cudaStream_t hstream;
+    cudaEvent_t h_after;
     float* s_actions;
     size_t s_actions_bytes;
-    void* s_obs;
+    void* s_block;         // device-side result block (obs | reward | flags)
+    size_t s_block_bytes;
     double* s_reward;
     uint8_t* s_done;
     uint8_t* s_trunc;
@@ -1685,6 +1925,7 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     h->d_stats = nullptr;
     h->n_sub = 1;
     h->n_graphs = 0;
+    h->graph_misses = 0;
     h->graph_clock = 0;
     h->fork_ev = nullptr;
     h->hi_stream = nullptr;
@@ -1695,7 +1936,9 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     h->hstream = nullptr;
     h->s_actions = nullptr;
     h->s_actions_bytes = 0;
-    h->s_obs = nullptr;
+    h->s_block = nullptr;
+    h->s_block_bytes = 0;
+    h->h_after = nullptr;
     h->s_reward = nullptr;
     h->s_done = h->s_trunc = nullptr;
     h->s_k = 0;
@@ -1754,6 +1997,12 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
             h->tev[k] = nullptr;
             if (h->timing && err == cudaSuccess) err = cudaEventCreate(&h->tev[k]);
         }
+        const char* env_pdl = getenv("SG_PDL");
+        h->use_pdl = env_pdl ? atoi(env_pdl) : 1;
+        const char* env_tail = getenv("SG_TAIL");
+        h->tail_mode = env_tail ? atoi(env_tail) : 2;
+        const char* env_tg = getenv("SG_TAIL_CTAS");
+        h->tail_grid = (env_tg && atoi(env_tg) > 0) ? atoi(env_tg) : 2;
         const char* env_pri = getenv("SG_PRIORITY");
         h->use_priority = env_pri ? atoi(env_pri) : 0;
         if (err == cudaSuccess) {
@@ -1806,7 +2055,8 @@ extern "C" void sg_destroy(sg_env* h) {
     if (h->ev_hot) cudaEventDestroy(h->ev_hot);
     if (h->ev_tail) cudaEventDestroy(h->ev_tail);
     if (h->s_actions) cudaFree(h->s_actions);
-    if (h->s_obs) cudaFree(h->s_obs);
+    if (h->s_block) cudaFree(h->s_block);
+    if (h->h_after) cudaEventDestroy(h->h_after);
     if (h->s_reward) cudaFree(h->s_reward);
     if (h->s_done) cudaFree(h->s_done);
     if (h->s_trunc) cudaFree(h->s_trunc);
@@ -1838,6 +2088,27 @@ extern "C" int sg_set_step_count(sg_env* h, uint64_t s) {
 }
 extern "C" int64_t sg_kernel_launches(const sg_env* h) { return h ? h->launches : 0; }
 
+// env.seed(seed) (spaceship_env.py:92-94, goal.py:74-77): re-key the per-env Philox streams.  Every env's draw
+// counter and the step counter that keys the synthetic-action stream restart at 0, so seed(s); reset(); ... replays
+// exactly what a handle created with seed s does.  Cached graphs hold the old key in their kernel parameters.
+extern "C" int sg_reseed(sg_env* h, uint64_t seed) {
+    if (!h) return SG_ERR_INVALID;
+    SG_CUDA(h, cudaSetDevice(h->device));
+    SG_CUDA(h, cudaDeviceSynchronize());
+    h->seed = seed;
+    build_dev(h);
+    for (int g = 0; g < h->n_graphs; ++g)
+        if (h->graphs[g].exec) cudaGraphExecDestroy(h->graphs[g].exec);
+    h->n_graphs = 0;
+    h->graph_misses = 0;
+    memset(h->graphs, 0, sizeof(h->graphs));
+    SG_CUDA(h, cudaMemset(h->dev.rng_ctr, 0, (size_t)h->n * sizeof(uint32_t)));
+    h->step_count = 0;
+    sync_step_counters(h, nullptr);
+    SG_CUDA(h, cudaDeviceSynchronize());
+    return SG_OK;
+}
+
 // debugging aid (SG_TIMING=1): mean milliseconds of {hot, continuation, tail} per env step so far
 extern "C" int sg_debug_kernel_times(sg_env* h, double out[6], int reset) {
     if (!h || !out) return SG_ERR_INVALID;
@@ -1868,18 +2139,41 @@ struct LaunchArgs {
     uint8_t* trunc;
     const uint8_t* mask;
     double* vf_out;
+    int obs_f32;     // dtype of `obs` for this call (the host result block may differ from the handle's obs_dtype)
+    int pack_flags;  // done | truncated << 1 in one byte (host result block)
     int sub;  // OP_STEP_SPLIT: sub-batch index
     cudaStream_t hi_stream;  // OP_STEP_SPLIT: stream of the small kernels (nullptr: same stream)
 };
+
+// Launch with (pdl = true) programmatic stream serialization: the grid may start while the previous kernel of the
+// stream drains; the kernels order themselves with pdl_wait().
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 template <class TR, typename OT>
 static void launch_typed(const sg_env* h, const LaunchArgs& a) {
     const int blocks = (int)((h->n + kBlock - 1) / kBlock);
     if (a.op == OP_STEP) {
-        step_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.K, a.step0, (OT*)a.obs, a.reward, a.done,
+        DevCfg dv = h->dev;
+        dv.pack_flags = a.pack_flags;
+        step_kernel<TR, OT><<<blocks, kBlock, 0, a.stream>>>(dv, a.actions, a.K, a.step0, (OT*)a.obs, a.reward, a.done,
                                                              a.trunc);
     } else if (a.op == OP_STEP_SPLIT) {
         const sg_env::Sub& sb = h->sub[a.sub];
+        DevCfg dv = sb.dev;  // kernel parameter of this launch
+        dv.pack_flags = a.pack_flags;
         const long long off = sb.off;
         const int sms = h->sm_count > 0 ? h->sm_count : 148;
         const int hot_blocks = (int)((sb.n + kBlock - 1) / kBlock);
@@ -1895,7 +2189,7 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         if (h->timing) cudaEventRecord(h->tev[0], a.stream);
         if (h->use_fused) {
             int fused_blocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
-            fused_kernel<TR, OT><<<fused_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
+            fused_kernel<TR, OT><<<fused_blocks, kBlock, 0, a.stream>>>(dv, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
         } else if (h->use_staged) {
             int pblocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
             static bool attr_set = false;  // per instantiation
@@ -1906,10 +2200,10 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
                                      cudaSharedmemCarveoutMaxShared);
                 attr_set = true;
             }
-            hot_staged_kernel<TR, OT><<<pblocks, kBlock, sizeof(HotPipeSmem<TR, OT>), a.stream>>>(sb.dev, act, obs, rew, dn, tr,
+            hot_staged_kernel<TR, OT><<<pblocks, kBlock, sizeof(HotPipeSmem<TR, OT>), a.stream>>>(dv, act, obs, rew, dn, tr,
                                                                                              (uint32_t)hot_blocks);
         } else {
-            hot_kernel<TR, OT><<<hot_blocks, kBlock, 0, a.stream>>>(sb.dev, act, obs, rew, dn, tr);
+            launch_k(hot_kernel<TR, OT>, hot_blocks, kBlock, a.stream, h->use_pdl != 0, dv, act, obs, rew, dn, tr);
         }
         if (h->timing) cudaEventRecord(h->tev[1], a.stream);
         cudaStream_t small = a.stream;
@@ -1920,11 +2214,12 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         }
         // step_plan 0 (default): hot -> generic continuation loop -> tail.  1: hot -> single-attempt continuation
         // -> loop for the rest -> tail.  2: fused persistent hot+continuation -> loop for the rest -> tail.
-        if (h->use_fused == 0 && h->use_cont1) cont1_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        if (h->use_fused == 0 && h->use_cont1) cont1_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(dv, act, obs, rew, dn, tr);
         if (h->use_fused || h->use_cont1)
-            cont_kernel<TR, OT><<<sms, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr, 1);
+            cont_kernel<TR, OT><<<sms, kBlock, 0, small>>>(dv, act, obs, rew, dn, tr, 1);
         else
-            cont_kernel<TR, OT><<<cont_blocks, kBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr, 0);
+            launch_k(cont_kernel<TR, OT>, cont_blocks, kBlock, small, h->use_pdl != 0 && !a.hi_stream, dv, act, obs, rew,
+                     dn, tr, 0);
         if (h->timing) {
             cudaEventRecord(h->tev[2], small);
             uint32_t qc[3] = {0, 0, 0};
@@ -1933,7 +2228,14 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
             for (int k = 0; k < 3; ++k) hm->q_acc[k] += qc[k];
             cudaEventRecord(h->tev[4], small);
         }
-        tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, small>>>(sb.dev, act, obs, rew, dn, tr);
+        if (h->tail_mode == 1) {
+            tail_kernel<TR, OT><<<tail_blocks, kTailBlock, 0, small>>>(dv, act, obs, rew, dn, tr);
+        } else {
+            const long long t2 = (sb.n + 31) / 32;
+            const int tail2_blocks = (int)(t2 < (long long)sms * h->tail_grid ? t2 : (long long)sms * h->tail_grid);
+            launch_k(tail2_kernel<TR, OT>, tail2_blocks, kTail2Block, small, h->use_pdl != 0 && !h->timing, dv, act, obs,
+                     rew, dn, tr);
+        }
         if (h->timing) {  // debugging aid: synchronous, never on in benchmarks
             cudaEventRecord(h->tev[3], small);
             cudaEventSynchronize(h->tev[3]);
@@ -1962,7 +2264,7 @@ static void launch_tr(const sg_env* h, const LaunchArgs& a) {
         vector_field_kernel<TR><<<blocks, kBlock, 0, a.stream>>>(h->dev, a.actions, a.vf_out);
         return;
     }
-    if (h->cfg.obs_dtype == SG_OBS_F32) launch_typed<TR, float>(h, a);
+    if (a.obs_f32) launch_typed<TR, float>(h, a);
     else launch_typed<TR, double>(h, a);
 }
 
@@ -1998,9 +2300,11 @@ template void launch_np<TASK_DNC, 1>(const sg_env*, const LaunchArgs&);
 static int enqueue(sg_env* h, const LaunchArgs& a) {
 #ifdef SG_DEV_ONLY_GOAL3P  // development builds (seconds instead of minutes): the BASELINE workload's instantiation only
     if (h->cfg.task == SG_TASK_GOAL && h->cfg.n_planets == 3 && h->cfg.ship_steering == SG_STEER_VELOCITY &&
-        !h->cfg.discrete && h->cfg.obs_dtype != SG_OBS_F32 && a.op != OP_VFIELD)
-        launch_typed<Traits<TASK_GOAL, 3, STEER_VEL, 0>, double>(h, a);
-    else return fail(h, SG_ERR_INVALID, "SG_DEV_ONLY_GOAL3P build: only GoalContinuous3P-v0 / f64 observations");
+        !h->cfg.discrete && a.op != OP_VFIELD) {
+        if (a.obs_f32) launch_typed<Traits<TASK_GOAL, 3, STEER_VEL, 0>, float>(h, a);
+        else launch_typed<Traits<TASK_GOAL, 3, STEER_VEL, 0>, double>(h, a);
+    }
+    else return fail(h, SG_ERR_INVALID, "SG_DEV_ONLY_GOAL3P build: only GoalContinuous3P-v0");
 #else
     if (h->cfg.task == SG_TASK_KEPLER) launch_np<TASK_KEPLER, 1>(h, a);
     else if (h->cfg.task == SG_TASK_DONOTCRASH) launch_np<TASK_DNC, 1>(h, a);
@@ -2051,19 +2355,26 @@ static int enqueue_split_step(sg_env* h, cudaStream_t origin, LaunchArgs a) {
 }
 
 // Same, replayed from a cached CUDA graph keyed by the argument pointers (one launch per env step).
-static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a) {
+static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a, bool may_graph) {
     SG_CUDA(h, cudaSetDevice(h->device));
-    if (!h->use_graphs || h->n_sub == 1) {  // graph replay of the 4-kernel chain measured slower than plain launches
+    // Graph replay only pays for the fork / join over several sub-batches, and only when the same argument pointers
+    // come back (single-step calls on persistent buffers).  The K steps of a multi-step call each have their own
+    // reward / done offsets (K distinct keys: every step would capture and instantiate), and a caller that passes
+    // fresh tensors every step never hits: after 32 consecutive misses the handle stops capturing.
+    if (!h->use_graphs || h->n_sub == 1 || !may_graph || h->graph_misses > 32) {
         int rc = enqueue_split_step(h, user, a);
         if (rc != SG_OK) return rc;
         SG_CUDA(h, cudaGetLastError());
         return SG_OK;
     }
-    const void* key[5] = {a.actions, a.obs, a.reward, a.done, a.trunc};
+    const void* key[6] = {a.actions, a.obs, a.reward, a.done, a.trunc,
+                          (const void*)(uintptr_t)(1u | (a.obs_f32 ? 2u : 0u) | (a.pack_flags ? 4u : 0u))};
     sg_env::GraphEntry* hit = nullptr;
     for (int g = 0; g < h->n_graphs; ++g)
         if (!memcmp(h->graphs[g].key, key, sizeof(key))) hit = &h->graphs[g];
+    if (hit) h->graph_misses = 0;
     if (!hit) {
+        h->graph_misses += 1;
         // capture is not allowed on the legacy default stream: capture on an internal one
         cudaStream_t origin = h->n_sub > 1 ? h->sub[0].stream : h->hi_stream;
         cudaGraph_t graph = nullptr;
@@ -2108,11 +2419,14 @@ extern "C" int sg_reset(sg_env* h, const uint8_t* d_mask, void* d_obs, void* str
     a.stream = (cudaStream_t)stream;
     a.mask = d_mask;
     a.obs = d_obs;
+    a.obs_f32 = h->cfg.obs_dtype == SG_OBS_F32;
     return launch(h, a);
 }
 
-extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, double* d_reward, uint8_t* d_done,
-                       uint8_t* d_truncated, void* stream) {
+// K env steps; obs_f32 / pack_flags describe the output buffers of THIS call (the host result block asks for
+// float32 observations and packed flags whatever the handle's obs_dtype is)
+static int step_impl(sg_env* h, const float* d_actions, int K, void* d_obs, int obs_f32, double* d_reward, uint8_t* d_done,
+                     uint8_t* d_truncated, int pack_flags, cudaStream_t stream) {
     if (!h || K <= 0) return SG_ERR_INVALID;
     if (d_obs && !aligned16(d_obs)) return fail(h, SG_ERR_INVALID, "sg_step: d_obs must be 16-byte aligned");
     if (d_actions && (((uintptr_t)d_actions) & 7u)) return fail(h, SG_ERR_INVALID, "sg_step: d_actions must be 8-byte aligned");
@@ -2121,7 +2435,9 @@ extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, do
     // kernel (3.3 vs 1.05 G env-steps/s on one 262144-env handle), whose warps pay for every rare path
     const bool split = (mode == SG_STEP_SPLIT) || (mode == SG_STEP_AUTO);
     LaunchArgs a{};
-    a.stream = (cudaStream_t)stream;
+    a.stream = stream;
+    a.obs_f32 = obs_f32;
+    a.pack_flags = pack_flags;
     if (!split) {
         a.op = OP_STEP;
         a.actions = d_actions;
@@ -2138,8 +2454,8 @@ extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, do
         SG_CUDA(h, cudaGetLastError());
         return SG_OK;
     }
-    // split path: K single steps (hot / continuation / tail kernels per sub-batch, replayed as one CUDA
-    // graph each); the observation is only needed after the last one
+    // split path: K single steps (hot / continuation / tail kernels per sub-batch); the observation is only
+    // needed after the last one
     a.op = OP_STEP_SPLIT;
     a.K = 1;
     for (int k = 0; k < K; ++k) {
@@ -2149,11 +2465,18 @@ extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, do
         a.reward = d_reward ? d_reward + off : nullptr;
         a.done = d_done ? d_done + off : nullptr;
         a.trunc = d_truncated ? d_truncated + off : nullptr;
-        int rc = launch_split_step(h, (cudaStream_t)stream, a);
+        int rc = launch_split_step(h, stream, a, K == 1);
         if (rc != SG_OK) return rc;
         h->step_count += 1;  // the tail kernels advance the device-side counters
     }
     return SG_OK;
+}
+
+extern "C" int sg_step(sg_env* h, const float* d_actions, int K, void* d_obs, double* d_reward, uint8_t* d_done,
+                       uint8_t* d_truncated, void* stream) {
+    if (!h) return SG_ERR_INVALID;
+    return step_impl(h, d_actions, K, d_obs, h->cfg.obs_dtype == SG_OBS_F32, d_reward, d_done, d_truncated, 0,
+                     (cudaStream_t)stream);
 }
 
 extern "C" int sg_vector_field(sg_env* h, const float* d_actions, double* d_out, void* stream) {
@@ -2166,53 +2489,123 @@ extern "C" int sg_vector_field(sg_env* h, const float* d_actions, double* d_out,
     return launch(h, a);
 }
 
-static size_t obs_elem(const sg_env* h) { return h->cfg.obs_dtype == SG_OBS_F32 ? 4 : 8; }
+// ---- host-buffer entry points --------------------------------------------------------------------------------
+// One device-side result block per handle, laid out like the host block the caller passes (sg_host_layout):
+//   obs [N][D] (f32 or f64) | reward f64 [N] | flags u8 [N] (bit 0 done, bit 1 truncated), 256-byte aligned parts.
+// A step is ONE host->device copy (actions), the step kernels, ONE device->host copy (the block), all on the
+// handle's own non-blocking stream.  That stream is ordered after `after_stream` (the stream the caller's other
+// work on this handle runs on: resets, set_state, device-path steps) by an event, so reset(); step(numpy) is safe.
+static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
-static int ensure_staging(sg_env* h, int K) {
+extern "C" int sg_host_block_layout(const sg_env* h, int obs_dtype, int want_obs, sg_host_layout* out) {
+    if (!h || !out) return SG_ERR_INVALID;
+    const int64_t n = h->n, D = sg_obs_dim(&h->cfg);
+    memset(out, 0, sizeof(*out));
+    out->obs_dtype = obs_dtype;
+    out->obs_dim = (int32_t)D;
+    out->n_envs = n;
+    int64_t off = 0;
+    out->obs = off;
+    off += want_obs ? align256(n * D * (obs_dtype == SG_OBS_F32 ? 4 : 8)) : 0;
+    out->reward = off;
+    off += align256(n * 8);
+    out->flags = off;
+    off += align256(n);
+    out->total_bytes = off;
+    return SG_OK;
+}
+
+static int ensure_host_path(sg_env* h, int K) {
     SG_CUDA(h, cudaSetDevice(h->device));
-    if (!h->hstream) SG_CUDA(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    if (!h->hstream) {
+        SG_CUDA(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+        SG_CUDA(h, cudaEventCreateWithFlags(&h->h_after, cudaEventDisableTiming));
+    }
     const size_t n = (size_t)h->n, D = (size_t)sg_obs_dim(&h->cfg);
-    if (!h->s_obs) SG_CUDA(h, cudaMalloc(&h->s_obs, n * D * obs_elem(h)));
-    if ((size_t)K > h->s_k) {
+    if (!h->s_block) {  // sized for the largest layout (f64 observations)
+        h->s_block_bytes = (size_t)(align256((int64_t)(n * D * 8)) + align256((int64_t)(n * 8)) + align256((int64_t)n));
+        SG_CUDA(h, cudaMalloc(&h->s_block, h->s_block_bytes));
+    }
+    if ((size_t)K > h->s_k) {  // legacy multi-step form: per-step reward / done / truncated rows
         if (h->s_actions) cudaFree(h->s_actions);
         if (h->s_reward) cudaFree(h->s_reward);
         if (h->s_done) cudaFree(h->s_done);
         if (h->s_trunc) cudaFree(h->s_trunc);
+        h->s_reward = nullptr;
+        h->s_done = h->s_trunc = nullptr;
         SG_CUDA(h, cudaMalloc((void**)&h->s_actions, (size_t)K * n * 2 * sizeof(float)));
-        SG_CUDA(h, cudaMalloc((void**)&h->s_reward, (size_t)K * n * sizeof(double)));
-        SG_CUDA(h, cudaMalloc((void**)&h->s_done, (size_t)K * n));
-        SG_CUDA(h, cudaMalloc((void**)&h->s_trunc, (size_t)K * n));
+        if (K > 1) {
+            SG_CUDA(h, cudaMalloc((void**)&h->s_reward, (size_t)K * n * sizeof(double)));
+            SG_CUDA(h, cudaMalloc((void**)&h->s_done, (size_t)K * n));
+            SG_CUDA(h, cudaMalloc((void**)&h->s_trunc, (size_t)K * n));
+        }
         h->s_k = (size_t)K;
     }
     return SG_OK;
 }
 
+// the handle's stream starts after everything enqueued so far on `after` (NULL: the legacy default stream, which
+// itself follows every blocking stream)
+static int order_after(sg_env* h, cudaStream_t after) {
+    SG_CUDA(h, cudaEventRecord(h->h_after, after));
+    SG_CUDA(h, cudaStreamWaitEvent(h->hstream, h->h_after, 0));
+    return SG_OK;
+}
+
+extern "C" int sg_step_host_block_async(sg_env* h, const float* h_actions, void* h_block, int obs_dtype, int want_obs,
+                                        void* after_stream) {
+    if (!h || !h_block) return SG_ERR_INVALID;
+    if (obs_dtype != SG_OBS_F32 && obs_dtype != SG_OBS_F64) return fail(h, SG_ERR_INVALID, "sg_step_host_block_async: bad obs_dtype");
+    int rc = ensure_host_path(h, 1);
+    if (rc != SG_OK) return rc;
+    rc = order_after(h, (cudaStream_t)after_stream);
+    if (rc != SG_OK) return rc;
+    sg_host_layout lay;
+    sg_host_block_layout(h, obs_dtype, want_obs, &lay);
+    const size_t n = (size_t)h->n;
+    char* blk = (char*)h->s_block;
+    if (h_actions)
+        SG_CUDA(h, cudaMemcpyAsync(h->s_actions, h_actions, n * 2 * sizeof(float), cudaMemcpyHostToDevice, h->hstream));
+    rc = step_impl(h, h_actions ? h->s_actions : nullptr, 1, want_obs ? (void*)(blk + lay.obs) : nullptr,
+                   obs_dtype == SG_OBS_F32, (double*)(blk + lay.reward), (uint8_t*)(blk + lay.flags), nullptr, 1, h->hstream);
+    if (rc != SG_OK) return rc;
+    SG_CUDA(h, cudaMemcpyAsync(h_block, blk, (size_t)lay.total_bytes, cudaMemcpyDeviceToHost, h->hstream));
+    return SG_OK;
+}
+
+static size_t obs_elem(const sg_env* h) { return h->cfg.obs_dtype == SG_OBS_F32 ? 4 : 8; }
+
 extern "C" int sg_reset_host(sg_env* h, void* h_obs) {
     if (!h) return SG_ERR_INVALID;
-    int rc = ensure_staging(h, 1);
+    int rc = ensure_host_path(h, 1);
     if (rc != SG_OK) return rc;
-    rc = sg_reset(h, nullptr, h_obs ? h->s_obs : nullptr, h->hstream);
+    rc = order_after(h, nullptr);
+    if (rc != SG_OK) return rc;
+    rc = sg_reset(h, nullptr, h_obs ? h->s_block : nullptr, h->hstream);
     if (rc != SG_OK) return rc;
     if (h_obs)
-        SG_CUDA(h, cudaMemcpyAsync(h_obs, h->s_obs, (size_t)h->n * sg_obs_dim(&h->cfg) * obs_elem(h),
+        SG_CUDA(h, cudaMemcpyAsync(h_obs, h->s_block, (size_t)h->n * sg_obs_dim(&h->cfg) * obs_elem(h),
                                    cudaMemcpyDeviceToHost, h->hstream));
     SG_CUDA(h, cudaStreamSynchronize(h->hstream));
     return SG_OK;
 }
 
+// separate-array form (K steps; observation in the handle's obs_dtype): five copies down per call
 extern "C" int sg_step_host_async(sg_env* h, const float* h_actions, int K, void* h_obs, double* h_reward,
                                   uint8_t* h_done, uint8_t* h_truncated) {
     if (!h || K <= 0) return SG_ERR_INVALID;
-    int rc = ensure_staging(h, K);
+    int rc = ensure_host_path(h, K > 1 ? K : 2);
+    if (rc != SG_OK) return rc;
+    rc = order_after(h, nullptr);
     if (rc != SG_OK) return rc;
     const size_t n = (size_t)h->n, kn = (size_t)K * n;
     if (h_actions)
         SG_CUDA(h, cudaMemcpyAsync(h->s_actions, h_actions, kn * 2 * sizeof(float), cudaMemcpyHostToDevice, h->hstream));
-    rc = sg_step(h, h_actions ? h->s_actions : nullptr, K, h_obs ? h->s_obs : nullptr, h_reward ? h->s_reward : nullptr,
+    rc = sg_step(h, h_actions ? h->s_actions : nullptr, K, h_obs ? h->s_block : nullptr, h_reward ? h->s_reward : nullptr,
                  h_done ? h->s_done : nullptr, h_truncated ? h->s_trunc : nullptr, h->hstream);
     if (rc != SG_OK) return rc;
     if (h_obs)
-        SG_CUDA(h, cudaMemcpyAsync(h_obs, h->s_obs, n * sg_obs_dim(&h->cfg) * obs_elem(h), cudaMemcpyDeviceToHost,
+        SG_CUDA(h, cudaMemcpyAsync(h_obs, h->s_block, n * sg_obs_dim(&h->cfg) * obs_elem(h), cudaMemcpyDeviceToHost,
                                    h->hstream));
     if (h_reward) SG_CUDA(h, cudaMemcpyAsync(h_reward, h->s_reward, kn * sizeof(double), cudaMemcpyDeviceToHost, h->hstream));
     if (h_done) SG_CUDA(h, cudaMemcpyAsync(h_done, h->s_done, kn, cudaMemcpyDeviceToHost, h->hstream));

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import spaces
-from ._lib import SgLayout, check, lib
+from ._lib import SgHostLayout, SgLayout, check, lib
 from .registry import make_config
 
 
@@ -60,12 +60,21 @@ def allreduce_stats(vals):
 
 
 class BatchedSpaceEnv:
-    def __init__(self, env_id, num_envs, device="cuda:0", seed=0, first_env_index=0, copy=True, **kwargs):
-        """copy=True returns fresh tensors from step()/step_many() (gym.vector's default); copy=False returns
-        the engine's persistent output buffers, which the next step overwrites (stable pointers also let the
-        C library replay its cached CUDA graph for the step)."""
+    def __init__(self, env_id, num_envs, device="cuda:0", seed=0, first_env_index=0, copy=True, host_obs_dtype="float32",
+                 check_actions=True, **kwargs):
+        """copy=True returns fresh tensors / arrays from step() (gym.vector's default); copy=False returns the
+        engine's persistent output buffers, which the next step overwrites.
+
+        host_obs_dtype: dtype of the observation the HOST-buffer path (`step(numpy)`, `step_async/step_wait`) brings
+        back.  Default float32 — the dtype `observation_space` declares (spaceship_env.py:110-111) and what a policy
+        consumes; it halves the bytes that cross the host link.  "float64" returns the engine's full-precision rows.
+        The device path (`step(torch)`) is governed by `obs_dtype=` as before (default float64).
+
+        check_actions: assert `action_space.contains(action)` on every step like the reference (spaceship_env.py:71);
+        pass False on a hot loop (it reads the whole action batch)."""
         self._h = None
         self.copy = bool(copy)
+        self.check_actions = bool(check_actions)
         self._out = {}
         self.env_id = env_id
         self.cfg = make_config(env_id, **kwargs)
@@ -80,6 +89,9 @@ class BatchedSpaceEnv:
         self.first_env_index = int(first_env_index)
         self.obs_dim = self._L.sg_obs_dim(C.byref(self.cfg))
         self.obs_dtype = torch.float32 if self.cfg.obs_dtype == 1 else torch.float64
+        if host_obs_dtype not in ("float32", "float64"):
+            raise ValueError("host_obs_dtype must be 'float32' or 'float64'")
+        self.host_obs_dtype = host_obs_dtype
         lay = SgLayout()
         check(self._L.sg_state_layout(C.byref(self.cfg), self.num_envs, C.byref(lay)))
         self.layout = lay
@@ -92,6 +104,8 @@ class BatchedSpaceEnv:
                                     self.first_env_index, self._state.data_ptr(), C.byref(h)))
         self._h = h
         self._host = None
+        self._host_want_obs = True
+        self._flip = 0
         self._init_spaces()
 
     # ---- spaces (spaceship_env.py:102-111,183-214; kepler.py:158-170) -------------------------
@@ -132,28 +146,45 @@ class BatchedSpaceEnv:
 
     # ---- gym.vector API ---------------------------------------------------------------------------
     def seed(self, seed=None):
-        """env.seed (spaceship_env.py:92-94): streams are keyed (seed, global env index); takes effect now."""
-        raise NotImplementedError("pass seed= to the constructor; streams are counter-based per (seed, env)")
+        """env.seed (spaceship_env.py:92-94, goal.py:74-77): re-key the per-env random streams (keyed by
+        (seed, global env index)) and restart their counters; takes effect with the next reset / step.
+        `seed(s); reset()` replays what an env constructed with seed=s does.  Returns [seed] like the reference."""
+        if seed is None:
+            seed = int.from_bytes(__import__("os").urandom(8), "little") >> 1
+        self.seed_value = int(seed)
+        check(self._L.sg_reseed(self._h, self.seed_value), self._h)
+        return [self.seed_value]
 
     def reset(self, mask=None):
+        """Reset all envs (or those whose mask entry is non-zero); returns the observation of EVERY env (the
+        current one for envs outside the mask)."""
         obs = torch.empty((self.num_envs, self.obs_dim), dtype=self.obs_dtype, device=self.device)
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         check(self._L.sg_reset(self._h, self._ptr(mask), self._ptr(obs), self._stream()), self._h)
         return obs
 
-    def step(self, actions, check_actions=False):
+    def _assert_actions(self, a, is_torch):
+        """action_space.contains for the whole batch (spaceship_env.py:69-72): Box(-1, 1, (2,)) or Discrete(6)."""
+        if self.cfg.discrete:
+            idx = a[..., 0] if a.ndim >= 2 and a.shape[-1] == 2 else a
+            ok = ((idx >= 0) & (idx <= 5) & (idx == (idx.floor() if is_torch else np.floor(idx)))).all()
+            assert bool(ok), "action outside Discrete(6)"
+        else:
+            assert bool(((a >= -1) & (a <= 1)).all()), "action outside Box(-1, 1)"
+
+    def step(self, actions, check_actions=None):
         """obs [N, D], reward [N], done [N] (bool), info — one env.step for every env.
 
         torch CUDA actions run the device path; numpy actions run the host-buffer path
-        (sg_step_host) and return numpy arrays."""
+        (sg_step_host_block_async) and return numpy arrays."""
         if isinstance(actions, np.ndarray):
             return self._step_host(actions, check_actions)
         obs, rew, done, info = self.step_many(actions[None] if actions.dim() == 2 else actions.view(1, -1, 2),
                                               check_actions)
         return obs, rew[0], done[0], {"TimeLimit.truncated": info["TimeLimit.truncated"][0]}
 
-    def step_many(self, actions=None, check_actions=False, K=None, want_obs=True):
+    def step_many(self, actions=None, check_actions=None, K=None, want_obs=True):
         """K env steps per call (split kernels, or one fused launch with step_mode="fused"). actions: f32 [K, N, 2]
         (discrete: [..., 0] holds the index) or
         None with K given for synthetic random actions. Returns obs after the last step, reward [K, N],
@@ -162,28 +193,29 @@ class BatchedSpaceEnv:
         if actions is not None:
             K = actions.shape[0]
             self._check_dev(actions, torch.float32, (K, n, 2))
-            if check_actions:  # the reference asserts action_space.contains (spaceship_env.py:71)
-                if self.cfg.discrete:
-                    a0 = actions[..., 0]
-                    assert bool(((a0 >= 0) & (a0 <= 5) & (a0 == a0.floor())).all()), "action outside Discrete(6)"
-                else:
-                    assert bool(((actions >= -1) & (actions <= 1)).all()), "action outside Box(-1, 1)"
+            if self.check_actions if check_actions is None else check_actions:
+                self._assert_actions(actions, True)
         K = int(K)
-        if K not in self._out:
-            if len(self._out) > 4:
+        # two output sets per K, used alternately: with copy=False the arrays of the previous call stay valid
+        # for one more call (what a rollout loop needs: it reads step t's results while step t+1 runs)
+        key = (K, 0 if self.copy else self._flip)
+        self._flip = 1 - self._flip
+        if key not in self._out:
+            if len(self._out) > 8:
                 self._out.clear()
-            self._out[K] = dict(obs=torch.empty((n, self.obs_dim), dtype=self.obs_dtype, device=self.device),
-                                rew=torch.empty((K, n), dtype=torch.float64, device=self.device),
-                                done=torch.empty((K, n), dtype=torch.uint8, device=self.device),
-                                trunc=torch.empty((K, n), dtype=torch.uint8, device=self.device))
-        o = self._out[K]
+            self._out[key] = dict(obs=torch.empty((n, self.obs_dim), dtype=self.obs_dtype, device=self.device),
+                                  rew=torch.empty((K, n), dtype=torch.float64, device=self.device),
+                                  done=torch.empty((K, n), dtype=torch.bool, device=self.device),
+                                  trunc=torch.empty((K, n), dtype=torch.bool, device=self.device))
+        o = self._out[key]
         obs = o["obs"] if want_obs else None
+        # done / truncated are written as 0 / 1 bytes straight into torch.bool storage: no conversion pass
         check(self._L.sg_step(self._h, self._ptr(actions), K, self._ptr(obs), self._ptr(o["rew"]), self._ptr(o["done"]),
                               self._ptr(o["trunc"]), self._stream()), self._h)
-        rew, done, trunc = o["rew"], o["done"].bool(), o["trunc"].bool()
+        rew, done, trunc = o["rew"], o["done"], o["trunc"]
         if self.copy:
             obs = obs.clone() if obs is not None else None
-            rew = rew.clone()
+            rew, done, trunc = rew.clone(), done.clone(), trunc.clone()
         return obs, rew, done, {"TimeLimit.truncated": trunc}
 
     def rollout_random(self, K):
@@ -191,15 +223,25 @@ class BatchedSpaceEnv:
         check(self._L.sg_step(self._h, None, int(K), None, None, None, None, self._stream()), self._h)
 
     # ---- host-buffer path (numpy in, numpy out): gym.vector step_async / step_wait -------------------
+    # One pinned result block per env object, laid out by the C library (sg_host_layout): observation | reward |
+    # flags.  A step is one host->device copy (actions), the step kernels, one device->host copy (the block).
     def _host_buffers(self):
         if self._host is None:
             n, D = self.num_envs, self.obs_dim
-            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
-            self._host = dict(act=pin((n, 2), torch.float32), obs=pin((n, D), self.obs_dtype),
-                              rew=pin((n,), torch.float64), done=pin((n,), torch.uint8), trunc=pin((n,), torch.uint8))
-            self._host_np = {k: v.numpy() for k, v in self._host.items()}
-            self._host_np["done"] = self._host_np["done"].view(np.bool_)
-            self._host_np["trunc"] = self._host_np["trunc"].view(np.bool_)
+            f32 = self.host_obs_dtype == "float32"
+            lay = SgHostLayout()
+            check(self._L.sg_host_block_layout(self._h, 1 if f32 else 0, 1, C.byref(lay)), self._h)
+            block = torch.empty(lay.total_bytes, dtype=torch.uint8).pin_memory()
+            act = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+            bn = block.numpy()
+            odt = np.float32 if f32 else np.float64
+            self._host = dict(block=block, act=act, layout=lay, f32=f32)
+            self._host_np = dict(
+                act=act.numpy(),
+                obs=bn[lay.obs:lay.obs + n * D * np.dtype(odt).itemsize].view(odt).reshape(n, D),
+                rew=bn[lay.reward:lay.reward + n * 8].view(np.float64),
+                flags=bn[lay.flags:lay.flags + n],
+                done=np.empty(n, dtype=np.bool_), trunc=np.empty(n, dtype=np.bool_))
         return self._host, self._host_np
 
     @property
@@ -207,34 +249,48 @@ class BatchedSpaceEnv:
         """Pinned float32 [N, 2] action buffer: write actions here and call step_async(None) to skip a copy."""
         return self._host_buffers()[1]["act"]
 
-    def step_async(self, actions=None, check_actions=False):
+    def step_async(self, actions=None, check_actions=None, want_obs=True):
         """Upload `actions` (numpy [N, 2] float32, or [N] ints for discrete envs; None = already written to
-        `action_buffer`), step, and start downloading the results on the handle's own stream."""
+        `action_buffer`), step, and start downloading the result block on the handle's own stream (ordered after
+        the work already enqueued on the current torch stream).  want_obs=False leaves the observation on the
+        device (9 bytes per env come back instead of 9 + 4 D)."""
         hb, hn = self._host_buffers()
         if actions is not None:
             a = np.asarray(actions)
+            if self.check_actions if check_actions is None else check_actions:
+                self._assert_actions(a, False)
             if self.cfg.discrete and a.ndim == 1:
                 hn["act"][:, 0] = a
                 hn["act"][:, 1] = 0
             else:
-                if check_actions:  # the reference asserts action_space.contains (spaceship_env.py:71)
-                    assert a.shape == (self.num_envs, 2) and np.all(a >= -1) and np.all(a <= 1), \
-                        "action outside Box(-1, 1)"
+                assert a.shape == (self.num_envs, 2), f"expected actions of shape {(self.num_envs, 2)}, got {a.shape}"
                 np.copyto(hn["act"], a, casting="same_kind")
-        check(self._L.sg_step_host_async(self._h, self._ptr(hb["act"]), 1, self._ptr(hb["obs"]), self._ptr(hb["rew"]),
-                                         self._ptr(hb["done"]), self._ptr(hb["trunc"])), self._h)
+        self._host_want_obs = bool(want_obs)
+        check(self._L.sg_step_host_block_async(self._h, self._ptr(hb["act"]), self._ptr(hb["block"]),
+                                               1 if hb["f32"] else 0, 1 if want_obs else 0, self._stream()), self._h)
 
     def step_wait(self):
-        """Block until the results of step_async are in host memory. The returned arrays are the env's pinned
-        buffers (overwritten by the next step) unless copy=True."""
+        """Block until the results of step_async are in host memory. The returned arrays are views of the env's
+        pinned result block (overwritten by the next step) unless copy=True."""
         check(self._L.sg_host_wait(self._h), self._h)
         hn = self._host_np
-        obs, rew, done, trunc = hn["obs"], hn["rew"], hn["done"], hn["trunc"]
+        if self._host_want_obs:
+            obs, rew, flags = hn["obs"], hn["rew"], hn["flags"]
+        else:  # without the observation the block is reward | flags from offset 0
+            n = self.num_envs
+            bn = self._host["block"].numpy()
+            lay = SgHostLayout()
+            check(self._L.sg_host_block_layout(self._h, 1 if self._host["f32"] else 0, 0, C.byref(lay)), self._h)
+            obs, rew, flags = None, bn[lay.reward:lay.reward + n * 8].view(np.float64), bn[lay.flags:lay.flags + n]
+        done, trunc = hn["done"], hn["trunc"]
+        np.not_equal(flags, 0, out=done)   # bit 0 = done, bit 1 = truncated (implies done)
+        np.greater(flags, 1, out=trunc)
         if self.copy:
-            obs, rew, done, trunc = obs.copy(), rew.copy(), done.copy(), trunc.copy()
+            obs = None if obs is None else obs.copy()
+            rew, done, trunc = rew.copy(), done.copy(), trunc.copy()
         return obs, rew, done, {"TimeLimit.truncated": trunc}
 
-    def _step_host(self, actions, check_actions=False):
+    def _step_host(self, actions, check_actions=None):
         self.step_async(actions, check_actions)
         return self.step_wait()
 
