@@ -43,6 +43,7 @@ ENV_KW = {}
 ENVS_PER_STEP = 262144
 N_BATCHES = 16
 ACTION_SETS = 4
+GATE_MS = 2.0
 # SURVEY.md §8d contract figures for GoalContinuous3P-v0 (per env step, K=1, f64 observation)
 ALGO_BYTES_PER_STEP = 329.0
 ALGO_FLOPS_PER_STEP = 1215.0
@@ -133,6 +134,76 @@ def cpu_baseline(total_budget_s=12.0, n_envs=65536):
                       f"oracle/sg_oracle.c with {cores} OpenMP threads ({dt:.1f} s)"}
 
 
+def ref_python_worker(env_id, seconds, seed, max_steps):
+    """`bench.py --ref-worker`: one unmodified reference env (baseline/_ref/gym_space behind the gym shim of
+    oracle/gym), random actions, TimeLimit auto-reset (spaceship_env.py:59-78).  Prints one JSON line."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    import numpy as np
+    import gym
+    import gym_space  # noqa: F401
+    env = gym.make(env_id)
+    env.seed(seed)
+    env.reset()
+    rng = np.random.RandomState(seed)
+    acts = rng.uniform(-1, 1, size=(4096, 2)).astype(np.float32)
+    for k in range(20):  # warm-up (imports, first solve_ivp)
+        _, _, done, _ = env.step(acts[k])
+        if done:
+            env.reset()
+    steps, episodes = 0, 0
+    t0 = time.perf_counter()
+    while steps < max_steps and time.perf_counter() - t0 < seconds:
+        _, _, done, _ = env.step(acts[steps & 4095])
+        steps += 1
+        if done:
+            env.reset()
+            episodes += 1
+    print(json.dumps({"steps": steps, "seconds": time.perf_counter() - t0, "episodes": episodes}), flush=True)
+
+
+def cpu_baseline_python(seconds=3.0):
+    """The UNMODIFIED reference gym loop on the host cores: one env per worker process over
+    sched_getaffinity cores, random actions, TimeLimit(500) auto-reset, each worker wall-clocked after its own
+    import / warm-up; plus BASELINE configs[0] (GoalContinuous2P-v0, one env, 1000 steps)."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "gym_space")):
+        return {"unavailable": "baseline/_ref/gym_space not staged (python tools/install_ref.py in the authoring container)"}
+    cores = len(os.sched_getaffinity(0))
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+
+    def run(env_id, workers, secs, max_steps):
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", env_id, str(secs), str(100 + w),
+                                   str(max_steps)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+                 for w in range(workers)]
+        res = []
+        for p in procs:
+            try:
+                out, err = p.communicate(timeout=secs + 120)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                return None, "reference worker timed out"
+            if p.returncode != 0:
+                return None, (err.strip().splitlines() or ["reference worker failed"])[-1]
+            res.append(json.loads(out.strip().splitlines()[-1]))
+        return res, None
+
+    res, err = run(ENV_ID, cores, seconds, 1 << 30)
+    if err:
+        return {"unavailable": err}
+    steps = sum(r["steps"] for r in res)
+    value = sum(r["steps"] / r["seconds"] for r in res)
+    out = {"value": value, "unit": UNIT, "cores": cores, "kind": "_ref", "per_core": value / cores,
+           "sample": f"{ENV_ID}, unmodified gym_space (baseline/_ref) behind oracle/gym, one env per worker process x "
+                     f"{cores}, random f32 actions, TimeLimit auto-reset, {steps} env steps in {seconds:.0f} s per worker "
+                     f"({sum(r['episodes'] for r in res)} episodes)"}
+    res, err = run("GoalContinuous2P-v0", 1, 60.0, 1000)
+    if not err:
+        out["config0"] = {"workload": "GoalContinuous2P-v0 single env, random actions, 1000 steps on CPU (reference Python step)",
+                          "value": res[0]["steps"] / res[0]["seconds"], "unit": UNIT, "cores": 1, "steps": res[0]["steps"],
+                          "seconds": res[0]["seconds"]}
+    return out
+
+
 def run_reference(args):
     """Reference arm: CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -220,6 +291,7 @@ def run_b200(args):
             e.rollout_random(args.prewarm)  # untimed: steady-state mix of episode ages
     L = envs[0]._L
     stream = torch.cuda.current_stream(dev)
+    sm_hz = getattr(torch.cuda.get_device_properties(dev), "clock_rate", 1965000) * 1e3  # kHz -> Hz, for the gate
     # the env batches are independent: each one is stepped on its own stream, forked from / joined into the
     # stream that carries the timing events
     batch_streams = [torch.cuda.Stream(device=dev) for _ in range(N_BATCHES)]
@@ -263,6 +335,11 @@ def run_b200(args):
     if sampler:
         sampler.rows.clear()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Device-side gate in front of ev0: the stream spins for ~GATE_MS while the host enqueues ev0, the forks and the
+    # first ~100 steps behind it, so the device-timed region measures the GPU executing K steps and not the host's
+    # enqueue latency (the fork alone is 16 event record/wait pairs).  A long run is device-bound with or without it
+    # (17 us of host time against ~45 us of device time per step); a 20-step run is 1 ms of device time in total.
+    torch.cuda._sleep(int(GATE_MS * 1e-3 * sm_hz))
     ev0.record(stream)
     fork()
     for k in range(args.steps):
@@ -308,39 +385,79 @@ def run_b200(args):
     barrier()
 
     # ---- end to end: public API with host buffers (pinned), copies inside the timed region ----
-    # gym.vector step_async / step_wait over the same env batches: every step uploads its actions
-    # from host memory and downloads observation, reward, done and truncated into host memory.
-    e2e_steps = max(N_BATCHES, min(args.steps, 200) // N_BATCHES * N_BATCHES)
-    host_acts = [np.random.RandomState(7 + rank + i).uniform(-1, 1, size=(n, 2)).astype(np.float32)
+    # gym.vector step_async / step_wait over the same env batches: every step uploads its actions from pinned host
+    # memory (one H2D copy) and downloads ONE packed result block (observation | reward | done/truncated flags) into
+    # pinned host memory.  The observation comes back in float32 (what observation_space declares,
+    # spaceship_env.py:110-111; BatchedSpaceEnv's host-path default) — `e2e_f64obs` is the same with float64 rows.
+    # Time-bounded: whole rounds over the batches until E2E_SECONDS have passed.
+    host_acts = [torch.from_numpy(np.random.RandomState(7 + rank + i).uniform(-1, 1, size=(n, 2)).astype(np.float32)).pin_memory()
                  for i in range(ACTION_SETS)]
-    for e in envs:
-        e.copy = False  # results are read in place from the pinned buffers
-    for k in range(2 * N_BATCHES):
-        envs[k % N_BATCHES].step_async(host_acts[k % ACTION_SETS])
-        if k >= N_BATCHES - 1:
-            envs[(k + 1) % N_BATCHES].step_wait()
-    for b in range(1, N_BATCHES):
-        envs[b].step_wait()
+    blk = n * (D * 4 + 8 + 1)
+
+    def e2e_leg(batch_envs, seconds):
+        for e in batch_envs:
+            e.copy = False  # results are read in place from the pinned block
+        nb = len(batch_envs)
+        for k in range(2 * nb):  # warm-up: allocates the pinned blocks, two steps per batch
+            if k >= nb:
+                batch_envs[k % nb].step_wait()
+            batch_envs[k % nb].step_async(host_acts[k % ACTION_SETS], check_actions=False)
+        for e in batch_envs:
+            e.step_wait()
+        barrier()
+        t0 = time.perf_counter()
+        checksum, rounds = 0.0, 1
+        for b in range(nb):
+            batch_envs[b].step_async(host_acts[b % ACTION_SETS], check_actions=False)
+        while True:
+            more = time.perf_counter() - t0 < seconds  # decided once per round over the batches
+            for b in range(nb):
+                # results of this batch's previous step: consumed before its buffers are reused
+                obs, rew, done, info = batch_envs[b].step_wait()
+                checksum += float(rew[0]) + float(obs[-1, 0]) + float(done[-1])
+                if more:
+                    batch_envs[b].step_async(host_acts[(rounds + b) % ACTION_SETS], check_actions=False)
+            if not more:
+                break
+            rounds += 1
+        steps_done = rounds * nb
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(steps_done)], dtype=torch.float64, device=dev)
+        if world > 1:  # whole job: env steps of all ranks over the slowest rank's time
+            tmax = tt.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            return n * float(tt[1].item()) / float(tmax[0].item()), int(tt[1].item()) // world
+        return n * steps_done / dt, steps_done
+
+    e2e_value, e2e_steps = e2e_leg(envs, args.e2e_seconds)
+    h2d = n * 2 * 4
+    d2h = int(envs[0]._host["layout"].total_bytes)  # the block that is copied (256-byte aligned parts)
+
+    # plain pinned-copy ceiling of the same link, measured here: device->host copies of one result block per
+    # cudaMemcpyAsync, all ranks at once, nothing else running (tools/host_link_peak.py has the 1/2/4/8-GPU sweep)
+    link_host = [torch.empty(blk, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    link_dev = [torch.empty(blk, dtype=torch.uint8, device=dev) for _ in range(2)]
+    link_stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(link_stream):
+        for i in range(4):
+            link_host[i % 2].copy_(link_dev[i % 2], non_blocking=True)
     barrier()
     t0 = time.perf_counter()
-    checksum = 0.0
-    for k in range(e2e_steps):
-        b = k % N_BATCHES
-        if k >= N_BATCHES:  # results of this batch's previous step: consume before reusing its buffers
-            obs, rew, done, info = envs[b].step_wait()
-            checksum += float(rew[0]) + float(obs[-1, 0])
-        envs[b].step_async(host_acts[(k // N_BATCHES) % ACTION_SETS])
-    for b in range(N_BATCHES):
-        obs, rew, done, info = envs[b].step_wait()
-        checksum += float(rew[0]) + float(obs[-1, 0])
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    copies = 0
+    while time.perf_counter() - t0 < 0.4:
+        with torch.cuda.stream(link_stream):
+            for i in range(4):
+                link_host[i % 2].copy_(link_dev[i % 2], non_blocking=True)
+        link_stream.synchronize()
+        copies += 4
+    dt_link = time.perf_counter() - t0
+    tl = torch.tensor([copies * blk / dt_link / 1e9], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = total * e2e_steps / float(te.item())
-    h2d = n * 2 * 4
-    d2h = n * (D * 8 + 8 + 1 + 1)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+    link_gbs = float(tl.item())
+    del link_host, link_dev
 
     # ---- per-kernel durations, live (CUDA events on the launching stream; SG_TIMING handle) -------------
     kt = None
@@ -366,33 +483,17 @@ def run_b200(args):
         tenv.close()
         del flush
 
-    # ---- end to end with float32 observations (the dtype observation_space declares, spaceship_env.py:110) ----
-    e2e32 = None
+    # ---- end to end with float64 observation rows in the host block (full-precision rows; 2x the bytes) ----
+    e2e64 = None
     if not args.no_f32:
-        envs32 = [sg.make(ENV_ID, n, device=dev, seed=2000 + b, first_env_index=rank * n, copy=False,
-                          obs_dtype="float32", **ENV_KW) for b in range(N_BATCHES)]
-        for e in envs32:
+        envs64 = [sg.make(ENV_ID, n, device=dev, seed=2000 + b, first_env_index=rank * n, copy=False,
+                          host_obs_dtype="float64", **ENV_KW) for b in range(N_BATCHES)]
+        for e in envs64:
             e.reset()
-        for rep in range(2):
-            barrier()
-            t0 = time.perf_counter()
-            for k in range(e2e_steps):
-                b = k % N_BATCHES
-                if k >= N_BATCHES:
-                    obs, rew, done, info = envs32[b].step_wait()
-                    checksum += float(rew[0]) + float(obs[-1, 0])
-                envs32[b].step_async(host_acts[(k // N_BATCHES) % ACTION_SETS])
-            for b in range(N_BATCHES):
-                obs, rew, done, info = envs32[b].step_wait()
-                checksum += float(rew[0])
-            barrier()
-            dt32 = time.perf_counter() - t0
-        t32 = torch.tensor([dt32], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
-        e2e32 = {"value": total * e2e_steps / float(t32.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                 "d2h_bytes_per_step": n * (D * 4 + 8 + 1 + 1), "steps": e2e_steps}
-        for e in envs32:
+        v64, s64 = e2e_leg(envs64, min(args.e2e_seconds, 0.5))
+        e2e64 = {"value": v64, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": n * (D * 8 + 8 + 1), "steps": s64}
+        for e in envs64:
             e.close()
 
     stats = envs[0].stats(allreduce=world > 1)  # the engine's only collective: episode statistics
@@ -436,6 +537,8 @@ def run_b200(args):
             "config": {"workload": workload_name(n),
                        "step_path": "one sg_step call per step: hot / continuation / tail kernels",
                        "envs_per_gpu_per_step": n, "total_envs_per_step": total, "seed": args.seed,
+                       "timing": f"CUDA events on the stream the batch streams fork from / join into; the K steps are "
+                                 f"enqueued behind a {GATE_MS:.0f} ms device-side gate (host enqueue latency is outside the device-timed region)",
                        "l2": f"inputs larger than L2: {N_BATCHES} env batches stepped round-robin "
                              f"({N_BATCHES * n * (ALGO_BYTES_PER_STEP + 60) / 1e6:.0f} MB working set)",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
@@ -457,8 +560,13 @@ def run_b200(args):
             "kernel_times": kt,
             "single_handle": single,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchedSpaceEnv.step_async(numpy)/step_wait() -> sg_step_host_async/sg_host_wait, all env batches in flight"},
-            "e2e_f32obs": e2e32,
+                    "steps": e2e_steps, "obs_dtype": "float32",
+                    "link_gbs_measured": link_gbs, "frac": e2e_value * (d2h / n) / 1e9 / link_gbs,
+                    "link_how": f"pinned device->host cudaMemcpyAsync of {blk} B blocks, {world} rank(s) at once, 0.4 s, this run",
+                    "api": "BatchedSpaceEnv.step_async(pinned actions)/step_wait() -> sg_step_host_block_async/sg_host_wait: "
+                           "one H2D copy, hot/continuation/tail kernels, one D2H copy of the packed result block per step; "
+                           "all env batches in flight"},
+            "e2e_f64obs": e2e64,
             "gpu_launches": launches * world,
             "host_cpus_rank0": len(cpus),
             "clocks": clocks,
@@ -468,6 +576,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline_python"] = cpu_baseline_python()
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     for e in envs:
@@ -489,6 +598,8 @@ class C_double:
 
 
 def main():
+    if len(sys.argv) >= 6 and sys.argv[1] == "--ref-worker":
+        return ref_python_worker(sys.argv[2], float(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4000)
@@ -499,7 +610,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prewarm", type=int, default=128, help="untimed env steps per batch that bring the envs to their steady-state mix of episode ages before warm-up")
     ap.add_argument("--batches", type=int, default=None, help="independent env batches in flight (default 16)")
-    ap.add_argument("--no-f32", action="store_true", help="skip the float32-observation end-to-end leg")
+    ap.add_argument("--no-f32", action="store_true", help="skip the float64-observation end-to-end leg")
+    ap.add_argument("--e2e-seconds", type=float, default=0.6, help="wall-clock length of the end-to-end leg")
     ap.add_argument("--env-id", default=None, help="benchmark another registered id (default: the BASELINE workload)")
     ap.add_argument("--kwargs", default="{}", help="JSON dict of reference-style kwargs for --env-id")
     args = ap.parse_args()

@@ -200,6 +200,13 @@ int64_t sg_kernel_launches(const sg_env* env);       /* kernels launched by this
  * env step (CUDA events on the launching stream), out[3..5] = mean entries of the {continuation, event, post}
  * queues per step. */
 int sg_debug_kernel_times(sg_env* env, double out[6], int reset);
+/* Sanitizer substitute (compute-sanitizer is not available on the GPU pool): in a library built with
+ * -DSG_CHECK_QUEUES every split step asserts on the device that the queue counters are zero when the step starts
+ * and after its tail kernel, that every queue slot is below the capacity, that every queue entry is an env index
+ * consumed once, and that every env left the step exactly once through {finish, terminal event}.  out[0..5] = number
+ * of violations by kind (all zero = clean), out[6] = env steps checked, out[7] = 1.  In a normal build the call
+ * returns SG_ERR_INVALID. */
+int sg_debug_queue_check(sg_env* env, uint64_t out[8]);
 
 /* ---- measurement helpers ----------------------------------------------------- */
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), measured

@@ -378,6 +378,10 @@ int so_make_step(const so_config* cfg, const double* planets, const double act[2
     double K[7][6];
     double f[6];
     int n_steps = 0, n_rej = 0, event_index = -1;
+    /* smallest distance of a DISCRETE decision of this step from its threshold (test diagnostics: a divergence
+     * between two correct implementations is only legitimate where this is at rounding level) */
+    double margin = INFINITY;
+#define SO_MARGIN(v) do { double m_ = fabs(v); if (m_ < margin) margin = m_; } while (0)
 
     /* RK45.__init__: f0 (mutates y[5] in velocity mode), then select_initial_step */
     fun(&ctx, y, f);
@@ -390,6 +394,8 @@ int so_make_step(const so_config* cfg, const double* planets, const double act[2
         for (int i = 0; i < 6; ++i) tmp[i] = f[i] / scale[i];
         double d1 = rms6(tmp);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        SO_MARGIN((d0 - 1e-5) / 1e-5);
+        SO_MARGIN((d1 - 1e-5) / 1e-5);
         h0 = fmin(h0, T);
         for (int i = 0; i < 6; ++i) y1[i] = y[i] + h0 * 1.0 * f[i];
         fun(&ctx, y1, f1);
@@ -448,6 +454,7 @@ int so_make_step(const so_config* cfg, const double* planets, const double act[2
                 err[i] = dot * h / sc;
             }
             double error_norm = rms6(err);
+            SO_MARGIN(error_norm - 1);
             if (error_norm < 1) {
                 double factor;
                 if (error_norm == 0) factor = 10;
@@ -474,6 +481,7 @@ int so_make_step(const so_config* cfg, const double* planets, const double act[2
         int active[SO_MAX_PLANETS + 3];
         for (int i = 0; i < NE; ++i) {
             g_new[i] = event_value(cfg, planets, i, y);
+            SO_MARGIN(g_new[i]);
             int up = (g[i] <= 0) && (g_new[i] >= 0);
             int down = (g[i] >= 0) && (g_new[i] <= 0);
             active[i] = up || down;
@@ -523,7 +531,9 @@ finish:
         diag->n_rejected = n_rej;
         diag->event_index = event_index;
         diag->t_end = t;
+        diag->margin = margin;
     }
+#undef SO_MARGIN
     for (int i = 0; i < 6; ++i)
         if (!isfinite(y[i])) *status |= SO_ERR_NONFINITE;
     return done;
@@ -945,6 +955,10 @@ int so_step(const so_config* cfg, so_env* env, const float* raw_action, so_draws
     double r;
     if (cfg->task == SO_TASK_GOAL) {
         r = goal_reward_dense(cfg, env, last_xy);
+        if (diag) { /* goal.py:154 is a discrete decision too */
+            double m = fabs(norm2(env->goal[0] - env->y[0], env->goal[1] - env->y[1]) - cfg->goal_radius);
+            if (m < diag->margin) diag->margin = m;
+        }
         if (norm2(env->goal[0] - env->y[0], env->goal[1] - env->y[1]) < cfg->goal_radius) {
             r += cfg->goal_sparse_reward;
             reached = 1;

@@ -72,6 +72,8 @@ typedef struct so_env {
 typedef struct so_step_diag {
     int32_t nfev, n_steps, n_rejected, event_index; /* event_index = -1: none */
     double t_end;
+    double margin; /* min |decision value - threshold| over the step's discrete decisions (accept/reject, event signs,
+                      the h0 branch, goal reached); rounding-level margins are where two correct implementations may part */
 } so_step_diag;
 
 /* status bits */

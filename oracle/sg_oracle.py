@@ -44,7 +44,7 @@ class Env(C.Structure):
 
 class Diag(C.Structure):
     _fields_ = [("nfev", C.c_int32), ("n_steps", C.c_int32), ("n_rejected", C.c_int32),
-                ("event_index", C.c_int32), ("t_end", C.c_double)]
+                ("event_index", C.c_int32), ("t_end", C.c_double), ("margin", C.c_double)]
 
 
 class Draws(C.Structure):
@@ -147,7 +147,7 @@ def step_transition(cfg, state, planets, goal, orbit, raw_action, goal_draws=Non
                      C.byref(reached), C.byref(diag))
     return dict(state1=np.array(env.y[:]), obs=obs, reward=rew.value, done=bool(done),
                 goal_reached=bool(reached.value), nfev=diag.nfev, n_steps=diag.n_steps, event=diag.event_index,
-                t_end=diag.t_end, status=env.status)
+                t_end=diag.t_end, margin=diag.margin, status=env.status)
 
 
 class Engine:

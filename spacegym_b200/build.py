@@ -56,5 +56,22 @@ def build(force=False, verbose=False, single=False):
     return OUT
 
 
+CHECK_OUT = os.path.join(HERE, "libspacegym_b200_check.so")
+
+
+def build_check(force=False):
+    """The sanitizer-substitute build (tests/test_gpu_queue_check.py): the same engine compiled with
+    -DSG_CHECK_QUEUES (device-side invariant counters on the work queues of the split step), BASELINE
+    instantiation only (GoalContinuous3P-v0; one translation unit, ~25 s)."""
+    if not force and os.path.exists(CHECK_OUT) and all(os.path.getmtime(s) <= os.path.getmtime(CHECK_OUT) for s in SRC):
+        return CHECK_OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DSG_CHECK_QUEUES", "-DSG_DEV_ONLY_GOAL3P", "-shared", SRC[0], "-o",
+                                                 CHECK_OUT + ".tmp"])
+    os.replace(CHECK_OUT + ".tmp", CHECK_OUT)
+    return CHECK_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, single="--single" in sys.argv))
+    print(build_check(force="--force" in sys.argv))

@@ -149,6 +149,43 @@ constexpr double P62 = -282668133.0 / 205662961.0, P63 = 2019193451.0 / 61698888
                  P64 = -1453857185.0 / 822651844.0;
 constexpr double P72 = 40617522.0 / 29380423.0, P73 = -110615467.0 / 29380423.0, P74 = 69997945.0 / 29380423.0;
 
+// ---- the hot path's constants in the constant bank ---------------------------------------------------------------
+// A 64-bit literal that is not representable as a 32-bit high-word immediate costs two UMOV (or two IMAD.MOV) every
+// time ptxas materialises it: the round-1 histogram of the hot kernel counted 270 UMOV + ~50 immediate moves per
+// warp and step against 564 DFMA.  Read from __constant__ memory the same values arrive two per LDCU.128 in
+// uniform registers, which the FP64 instructions take directly as an operand.  HT(name) selects the source;
+// -DSG_NO_CONST_BANK keeps the literals (A/B builds).  Cold code (dense output, roots, resets) keeps the literals.
+struct HotTab {
+    double c2, c3, c4, c5, cs3, cs4, cs5, cs6, cs7;
+    double c2x2, pad0;
+    double ab31, ab41, ab42, ab51, ab52, ab53, ab61, ab62, ab63, ab64;
+    double bb1, bb2, bb3, bb4, bb5, b1, b3, b4, b5, b6;
+    double eb1, eb2, eb3, eb4, eb5, eb6, e1, e3, e4, e5, e6, e7;
+    double rtol, atol, sixth, pad1;
+    double ts[6];  // sin Taylor: 1/13!, -1/11!, 1/9!, -1/7!, 1/5!, -1/3!
+    double tc[6];  // cos Taylor: -1/14!, 1/12!, -1/10!, 1/8!, -1/6!, 1/4!
+};
+static __constant__ HotTab kHot = {
+    c2, c3, c4, c5, cs3, cs4, cs5, cs6, cs7,
+    2 * c2, 0.0,
+    ab31, ab41, ab42, ab51, ab52, ab53, ab61, ab62, ab63, ab64,
+    bb1, bb2, bb3, bb4, bb5, b1, b3, b4, b5, b6,
+    eb1, eb2, eb3, eb4, eb5, eb6, e1, e3, e4, e5, e6, e7,
+    kRtol, kAtol, 1.0 / 6.0, 0.0,
+    {1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0},
+    {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0},
+};
+#ifndef SG_NO_CONST_BANK
+#define HT(name) (kHot.name)
+#define HTS(k) (kHot.ts[k])
+#define HTC(k) (kHot.tc[k])
+#else
+#define HT(name) (name)
+#define HTS(k) (k == 0 ? 1.0 / 6227020800.0 : k == 1 ? -1.0 / 39916800.0 : k == 2 ? 1.0 / 362880.0 : k == 3 ? -1.0 / 5040.0 : k == 4 ? 1.0 / 120.0 : -1.0 / 6.0)
+#define HTC(k) (k == 0 ? -1.0 / 87178291200.0 : k == 1 ? 1.0 / 479001600.0 : k == 2 ? -1.0 / 3628800.0 : k == 3 ? 1.0 / 40320.0 : k == 4 ? -1.0 / 720.0 : 1.0 / 24.0)
+#endif
+constexpr double rtol = kRtol, atol = kAtol, sixth = 1.0 / 6.0;  // literal names behind HT()
+
 // ---- engine constants, passed to kernels by value ------------------------------------------
 struct DevCfg {
     // struct-of-arrays state (include/spacegym_b200.h: sg_layout)
@@ -180,11 +217,22 @@ struct DevCfg {
     unsigned long long seed;
     int max_episode_steps, randomize, auto_reset, rows, cols;
     int pack_flags;  // 1: done_out holds done | truncated << 1 in one byte per env (host result block), trunc_out unused
+#ifdef SG_CHECK_QUEUES
+    // -DSG_CHECK_QUEUES (debug build, tests/test_gpu_queue_check.py): device-side invariants of the split step's work
+    // queues, counted instead of trapped.  chk_err[k]: 0 queue counters not zero when a step starts, 1 queue slot >=
+    // capacity, 2 an env did not leave its step exactly once through {finish, event}, 3 an env consumed twice from the
+    // same queue in one step, 4 queue entry is not an env index, 5 queue counters not zero after the tail kernel.
+    uint32_t* chk_err;     // [8]
+    uint32_t* chk_visits;  // [N]: step exits per env since the handle was created
+    uint32_t* chk_mark;    // [3][N]: epoch of the last consumption from the continuation / event / post queue
+    uint32_t chk_epoch;    // steps checked so far + 1
+#endif
     // physics
     double T, half_ws, two_over_ws, om_max, inv_mass, moi;
     double max_engine, max_thruster;          // float64 action path (discrete)
     float max_engine_f32, max_thruster_f32;   // float32 action path (continuous)
     double gm0;                               // G * m_ship * M_planet (all Goal planets equal)
+    double gmm;                               // gm0 / m_ship: the acceleration form the force evaluations use
     double r0, r1;                            // event radii: Goal planets r0; Kepler planet r0, border r1
     // Goal reward
     double survival, goal_vel, safety, sparse, danger_zone, goal_radius, ship_radius;
@@ -335,9 +383,27 @@ __device__ __forceinline__ Act translate_action(const DevCfg& c, float r0, float
 // ---- forces (dynamic_model.py:145-176, helpers.py:22-35) -----------------------------------------
 // a = (-(cos th, sin th) fs + sum_p GM d_p / |d_p|^3) / m.  The Kepler border has mass 0 and
 // contributes exactly 0, so it is not a gravitating body here.
+// |d|^-3 from d2 = |d|^2: hardware rsqrt seed y (~2^-22) and ONE correction of the -3/2 power,
+// d2^(-3/2) = y^3 (1 - e)^(-3/2) = y^3 (1 + 3/2 e + 15/8 e^2 + O(e^3)), e = 1 - d2 y^2 (|e| < 5e-7: the dropped term is
+// < 3e-19).  The force only needs the cube, so this replaces rsqrt-to-full-precision followed by two multiplies: the
+// dependent chain behind the MUFU is 4 FP64 operations instead of 7.  Built with -DSG_SHORT_CHAIN only: measured
+// neutral (5.735e9 vs 5.726e9 env-steps/s, profiles/r2_notes.md) — four warps per scheduler already saturate the
+// FP64 pipe on dependent DFMA chains (tools/micro/fp64_latency.cu: 8-cycle latency, one DFMA per 2 cycles), so the
+// chain length is not what the hot kernel waits for.  The round-1 form stays the default.
+__device__ __forceinline__ double inv_cube(double d2) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2));
+    const double y2 = y * y;
+    const double e = fma(-d2, y2, 1.0);
+    const double y3 = y2 * y;
+    const double p = fma(e, 1.875, 1.5);
+    return fma(y3 * e, p, y3);
+}
+
 template <class TR>
 __device__ __forceinline__ void accel(const DevCfg& c, const EnvRegs<TR>& e, double x, double y, double cth,
                                       double sth, double fs, double& ax, double& ay) {
+#ifndef SG_SHORT_CHAIN
     double fx = -cth * fs, fy = -sth * fs;
 #pragma unroll
     for (int p = 0; p < TR::NP; ++p) {
@@ -349,6 +415,21 @@ __device__ __forceinline__ void accel(const DevCfg& c, const EnvRegs<TR>& e, dou
     }
     ax = fx * c.inv_mass;
     ay = fy * c.inv_mass;
+#else
+    // thrust and GM already divided by the ship's mass (both products are common to every force evaluation of the
+    // step: computed once); the planets' terms accumulate onto the thrust term
+    const double fsm = fs * c.inv_mass;
+    double fx = -cth * fsm, fy = -sth * fsm;
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        const double dx = e.px[p] - x, dy = e.py[p] - y;
+        const double s = c.gmm * inv_cube(fma(dx, dx, dy * dy));
+        fx = fma(dx, s, fx);
+        fy = fma(dy, s, fy);
+    }
+    ax = fx;
+    ay = fy;
+#endif
 }
 
 template <class TR>
@@ -360,6 +441,7 @@ template <class TR>
 __device__ __forceinline__ void accel_pd(const DevCfg& c, const EnvRegs<TR>& e, double x, double y, double cth,
                                          double sth, double fs, double& ax, double& ay, double (&pd)[TR::NP],
                                          double (&ipd)[TR::NP]) {
+#ifndef SG_SHORT_CHAIN
     double fx = -cth * fs, fy = -sth * fs;
 #pragma unroll
     for (int p = 0; p < TR::NP; ++p) {
@@ -375,6 +457,30 @@ __device__ __forceinline__ void accel_pd(const DevCfg& c, const EnvRegs<TR>& e, 
     }
     ax = fx * c.inv_mass;
     ay = fy * c.inv_mass;
+#else
+    const double fsm = fs * c.inv_mass;
+    double fx = -cth * fsm, fy = -sth * fsm;
+#pragma unroll
+    for (int p = 0; p < TR::NP; ++p) {
+        const double dx = e.px[p] - x, dy = e.py[p] - y;
+        const double d2 = fma(dx, dx, dy * dy);
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d2));
+        const double y2 = y0 * y0;
+        const double er = fma(-d2, y2, 1.0);
+        const double y3 = y2 * y0;
+        // force: the cube directly (as inv_cube); distance and its inverse from the same seed, off the force's chain
+        const double s = c.gmm * fma(y3 * er, fma(er, 1.875, 1.5), y3);
+        fx = fma(dx, s, fx);
+        fy = fma(dy, s, fy);
+        const double inv = fma(y0 * er, fma(er, 0.375, 0.5), y0);
+        const double sq = d2 * inv;
+        pd[p] = fma(fma(-sq, sq, d2), 0.5 * inv, sq);  // fast_sqrt(d2)
+        ipd[p] = inv;
+    }
+    ax = fx;
+    ay = fy;
+#endif
 }
 
 // ---- termination events (dynamic_model.py:183-217) -------------------------------------------------
@@ -609,17 +715,14 @@ struct Integ {
 __device__ __forceinline__ void small_sincos(double d, bool small, double& sn, double& cs) {
     if (small) {
         const double d2 = d * d;
-        double ps = fma(d2, 1.0 / 6227020800.0, -1.0 / 39916800.0);
-        ps = fma(ps, d2, 1.0 / 362880.0);
-        ps = fma(ps, d2, -1.0 / 5040.0);
-        ps = fma(ps, d2, 1.0 / 120.0);
-        ps = fma(ps, d2, -1.0 / 6.0);
+        double ps = fma(d2, HTS(0), HTS(1));
+        double pc = fma(d2, HTC(0), HTC(1));
+#pragma unroll
+        for (int k = 2; k < 6; ++k) {
+            ps = fma(ps, d2, HTS(k));
+            pc = fma(pc, d2, HTC(k));
+        }
         sn = fma(ps * d2, d, d);
-        double pc = fma(d2, -1.0 / 87178291200.0, 1.0 / 479001600.0);
-        pc = fma(pc, d2, -1.0 / 3628800.0);
-        pc = fma(pc, d2, 1.0 / 40320.0);
-        pc = fma(pc, d2, -1.0 / 720.0);
-        pc = fma(pc, d2, 1.0 / 24.0);
         pc = fma(pc, d2, -0.5);
         cs = fma(pc, d2, 1.0);
     } else {
@@ -654,9 +757,9 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     double ipd0[TR::NP];
     accel_pd<TR>(c, e, S.x, S.y, S.cth, S.sth, S.fs, S.Ax, S.Ay, pd, ipd0);  // f0 (+ planet distances for g(t0))
     const double x = S.x, y = S.y, th = S.th, vx = S.vx, vy = S.vy, om = S.om, alpha = S.alpha;
-    double rx = fast_rcp(kAtol + fabs(x) * kRtol), ry = fast_rcp(kAtol + fabs(y) * kRtol);
-    double rth = fast_rcp(kAtol + fabs(th) * kRtol), rvx = fast_rcp(kAtol + fabs(vx) * kRtol);
-    double rvy = fast_rcp(kAtol + fabs(vy) * kRtol), rom = fast_rcp(kAtol + fabs(om) * kRtol);
+    double rx = fast_rcp(HT(atol) + fabs(x) * HT(rtol)), ry = fast_rcp(HT(atol) + fabs(y) * HT(rtol));
+    double rth = fast_rcp(HT(atol) + fabs(th) * HT(rtol)), rvx = fast_rcp(HT(atol) + fabs(vx) * HT(rtol));
+    double rvy = fast_rcp(HT(atol) + fabs(vy) * HT(rtol)), rom = fast_rcp(HT(atol) + fabs(om) * HT(rtol));
     double q, S0 = 0, S1 = 0, S2 = 0;
     q = x * rx; S0 = fma(q, q, S0);
     q = y * ry; S0 = fma(q, q, S0);
@@ -724,17 +827,17 @@ __device__ __forceinline__ void small_sincos_n(const double (&d)[N], bool small,
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             d2[j] = d[j] * d[j];
-            ps[j] = fma(d2[j], 1.0 / 6227020800.0, -1.0 / 39916800.0);
-            pc[j] = fma(d2[j], -1.0 / 87178291200.0, 1.0 / 479001600.0);
+            ps[j] = fma(d2[j], HTS(0), HTS(1));
+            pc[j] = fma(d2[j], HTC(0), HTC(1));
         }
 #pragma unroll
-        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], 1.0 / 362880.0); pc[j] = fma(pc[j], d2[j], -1.0 / 3628800.0); }
+        for (int k = 2; k < 6; ++k) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], -1.0 / 5040.0); pc[j] = fma(pc[j], d2[j], 1.0 / 40320.0); }
-#pragma unroll
-        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], 1.0 / 120.0); pc[j] = fma(pc[j], d2[j], -1.0 / 720.0); }
-#pragma unroll
-        for (int j = 0; j < N; ++j) { ps[j] = fma(ps[j], d2[j], -1.0 / 6.0); pc[j] = fma(pc[j], d2[j], 1.0 / 24.0); }
+            for (int j = 0; j < N; ++j) {
+                ps[j] = fma(ps[j], d2[j], HTS(k));
+                pc[j] = fma(pc[j], d2[j], HTC(k));
+            }
+        }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             sn[j] = fma(ps[j] * d2[j], d[j], d[j]);
@@ -766,12 +869,12 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     const double hh = h * h, ho = h * S.om, ha = hh * S.alpha;
     const bool small = fabs(ho) + fabs(ha) < 0.5;
     double d[6], sd[6], cd[6];
-    d[0] = c2 * ho;
-    d[1] = c3 * ho + cs3 * ha;
-    d[2] = c4 * ho + cs4 * ha;
-    d[3] = c5 * ho + cs5 * ha;
-    d[4] = ho + cs6 * ha;
-    d[5] = ho + cs7 * ha;
+    d[0] = HT(c2) * ho;
+    d[1] = HT(c3) * ho + HT(cs3) * ha;
+    d[2] = HT(c4) * ho + HT(cs4) * ha;
+    d[3] = HT(c5) * ho + HT(cs5) * ha;
+    d[4] = ho + HT(cs6) * ha;
+    d[5] = ho + HT(cs7) * ha;
     if (TR::STEER == STEER_VEL && small) {
         // velocity steering: alpha = 0, so the increments are c_i h omega with c = 1/5, 3/10, 4/5, 8/9, 1, 1.
         // Three polynomials (a = d[0], d[1], d[3]) instead of six: 4a by two angle doublings, 5a = 4a + a by one
@@ -800,34 +903,74 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     }
     Ax[0] = S.Ax;
     Ay[0] = S.Ay;
-    accel(c, e, x + (c2 * h) * vx, y + (c2 * h) * vy, cr[0], sr[0], S.fs, Ax[1], Ay[1]);
-    accel(c, e, x + (c3 * h) * vx + hh * (ab31 * Ax[0]), y + (c3 * h) * vy + hh * (ab31 * Ay[0]), cr[1], sr[1], S.fs,
+#ifndef SG_SHORT_CHAIN
+    accel(c, e, x + (HT(c2) * h) * vx, y + (HT(c2) * h) * vy, cr[0], sr[0], S.fs, Ax[1], Ay[1]);
+    accel(c, e, x + (HT(c3) * h) * vx + hh * (HT(ab31) * Ax[0]), y + (HT(c3) * h) * vy + hh * (HT(ab31) * Ay[0]), cr[1], sr[1], S.fs,
           Ax[2], Ay[2]);
-    accel(c, e, x + (c4 * h) * vx + hh * (ab41 * Ax[0] + ab42 * Ax[1]),
-          y + (c4 * h) * vy + hh * (ab41 * Ay[0] + ab42 * Ay[1]), cr[2], sr[2], S.fs, Ax[3], Ay[3]);
-    accel(c, e, x + (c5 * h) * vx + hh * (ab51 * Ax[0] + ab52 * Ax[1] + ab53 * Ax[2]),
-          y + (c5 * h) * vy + hh * (ab51 * Ay[0] + ab52 * Ay[1] + ab53 * Ay[2]), cr[3], sr[3], S.fs, Ax[4], Ay[4]);
-    accel(c, e, x + h * vx + hh * (ab61 * Ax[0] + ab62 * Ax[1] + ab63 * Ax[2] + ab64 * Ax[3]),
-          y + h * vy + hh * (ab61 * Ay[0] + ab62 * Ay[1] + ab63 * Ay[2] + ab64 * Ay[3]), cr[4], sr[4], S.fs, Ax[5],
+    accel(c, e, x + (HT(c4) * h) * vx + hh * (HT(ab41) * Ax[0] + HT(ab42) * Ax[1]),
+          y + (HT(c4) * h) * vy + hh * (HT(ab41) * Ay[0] + HT(ab42) * Ay[1]), cr[2], sr[2], S.fs, Ax[3], Ay[3]);
+    accel(c, e, x + (HT(c5) * h) * vx + hh * (HT(ab51) * Ax[0] + HT(ab52) * Ax[1] + HT(ab53) * Ax[2]),
+          y + (HT(c5) * h) * vy + hh * (HT(ab51) * Ay[0] + HT(ab52) * Ay[1] + HT(ab53) * Ay[2]), cr[3], sr[3], S.fs, Ax[4], Ay[4]);
+    accel(c, e, x + h * vx + hh * (HT(ab61) * Ax[0] + HT(ab62) * Ax[1] + HT(ab63) * Ax[2] + HT(ab64) * Ax[3]),
+          y + h * vy + hh * (HT(ab61) * Ay[0] + HT(ab62) * Ay[1] + HT(ab63) * Ay[2] + HT(ab64) * Ay[3]), cr[4], sr[4], S.fs, Ax[5],
           Ay[5]);
-    xn = x + h * vx + hh * (bb1 * Ax[0] + bb2 * Ax[1] + bb3 * Ax[2] + bb4 * Ax[3] + bb5 * Ax[4]);
-    yn = y + h * vy + hh * (bb1 * Ay[0] + bb2 * Ay[1] + bb3 * Ay[2] + bb4 * Ay[3] + bb5 * Ay[4]);
-    vxn = vx + h * (b1 * Ax[0] + b3 * Ax[2] + b4 * Ax[3] + b5 * Ax[4] + b6 * Ax[5]);
-    vyn = vy + h * (b1 * Ay[0] + b3 * Ay[2] + b4 * Ay[3] + b5 * Ay[4] + b6 * Ay[5]);
+    xn = x + h * vx + hh * (HT(bb1) * Ax[0] + HT(bb2) * Ax[1] + HT(bb3) * Ax[2] + HT(bb4) * Ax[3] + HT(bb5) * Ax[4]);
+    yn = y + h * vy + hh * (HT(bb1) * Ay[0] + HT(bb2) * Ay[1] + HT(bb3) * Ay[2] + HT(bb4) * Ay[3] + HT(bb5) * Ay[4]);
+    vxn = vx + h * (HT(b1) * Ax[0] + HT(b3) * Ax[2] + HT(b4) * Ax[3] + HT(b5) * Ax[4] + HT(b6) * Ax[5]);
+    vyn = vy + h * (HT(b1) * Ay[0] + HT(b3) * Ay[2] + HT(b4) * Ay[3] + HT(b5) * Ay[4] + HT(b6) * Ay[5]);
+#else
+    // Stage positions x_i = x + c_i h vx + h^2 sum_k ab_ik A_k, accumulated term by term with the NEWEST force last:
+    // everything but the final fma of a stage depends only on older forces and is off the critical path
+    // (h^2 ab_ik are formed once per attempt).  One fma then separates A_{i-1} from the position it is needed at.
+    {
+        const double bx1 = fma(HT(c2) * h, vx, x), by1 = fma(HT(c2) * h, vy, y);
+        accel(c, e, bx1, by1, cr[0], sr[0], S.fs, Ax[1], Ay[1]);
+        const double h31 = hh * HT(ab31);
+        const double h41 = hh * HT(ab41), h42 = hh * HT(ab42);
+        const double h51 = hh * HT(ab51), h52 = hh * HT(ab52), h53 = hh * HT(ab53);
+        const double h61 = hh * HT(ab61), h62 = hh * HT(ab62), h63 = hh * HT(ab63), h64 = hh * HT(ab64);
+        const double g1 = hh * HT(bb1), g2 = hh * HT(bb2), g3 = hh * HT(bb3), g4 = hh * HT(bb4), g5 = hh * HT(bb5);
+        const double x3 = fma(h31, Ax[0], fma(HT(c3) * h, vx, x)), y3 = fma(h31, Ay[0], fma(HT(c3) * h, vy, y));
+        // partial sums over forces that already exist
+        double x4 = fma(h41, Ax[0], fma(HT(c4) * h, vx, x)), y4 = fma(h41, Ay[0], fma(HT(c4) * h, vy, y));
+        double x5 = fma(h51, Ax[0], fma(HT(c5) * h, vx, x)), y5 = fma(h51, Ay[0], fma(HT(c5) * h, vy, y));
+        const double xe = fma(h, vx, x), ye = fma(h, vy, y);
+        double x6 = fma(h61, Ax[0], xe), y6 = fma(h61, Ay[0], ye);
+        double x7 = fma(g1, Ax[0], xe), y7 = fma(g1, Ay[0], ye);
+        x4 = fma(h42, Ax[1], x4); y4 = fma(h42, Ay[1], y4);
+        x5 = fma(h52, Ax[1], x5); y5 = fma(h52, Ay[1], y5);
+        x6 = fma(h62, Ax[1], x6); y6 = fma(h62, Ay[1], y6);
+        x7 = fma(g2, Ax[1], x7); y7 = fma(g2, Ay[1], y7);
+        accel(c, e, x3, y3, cr[1], sr[1], S.fs, Ax[2], Ay[2]);
+        accel(c, e, x4, y4, cr[2], sr[2], S.fs, Ax[3], Ay[3]);
+        x5 = fma(h53, Ax[2], x5); y5 = fma(h53, Ay[2], y5);
+        x6 = fma(h63, Ax[2], x6); y6 = fma(h63, Ay[2], y6);
+        x7 = fma(g3, Ax[2], x7); y7 = fma(g3, Ay[2], y7);
+        accel(c, e, x5, y5, cr[3], sr[3], S.fs, Ax[4], Ay[4]);
+        x6 = fma(h64, Ax[3], x6); y6 = fma(h64, Ay[3], y6);
+        x7 = fma(g4, Ax[3], x7); y7 = fma(g4, Ay[3], y7);
+        accel(c, e, x6, y6, cr[4], sr[4], S.fs, Ax[5], Ay[5]);
+        xn = fma(g5, Ax[4], x7);
+        yn = fma(g5, Ay[4], y7);
+        const double k1 = h * HT(b1), k3 = h * HT(b3), k4 = h * HT(b4), k5 = h * HT(b5), k6 = h * HT(b6);
+        vxn = fma(k6, Ax[5], fma(k5, Ax[4], fma(k4, Ax[3], fma(k3, Ax[2], fma(k1, Ax[0], vx)))));
+        vyn = fma(k6, Ay[5], fma(k5, Ay[4], fma(k4, Ay[3], fma(k3, Ay[2], fma(k1, Ay[0], vy)))));
+    }
+#endif
     thn = S.th + d[5];
     omn = S.om + h * S.alpha;
     cn = cr[5];
     sn = sr[5];
     accel_pd<TR>(c, e, xn, yn, cn, sn, S.fs, Ax[6], Ay[6], pdn, ipdn);  // f_new (FSAL) + distances at the end point
-    double ex = hh * (eb1 * Ax[0] + eb2 * Ax[1] + eb3 * Ax[2] + eb4 * Ax[3] + eb5 * Ax[4] + eb6 * Ax[5]);
-    double ey = hh * (eb1 * Ay[0] + eb2 * Ay[1] + eb3 * Ay[2] + eb4 * Ay[3] + eb5 * Ay[4] + eb6 * Ay[5]);
-    double evx = h * (e1 * Ax[0] + e3 * Ax[2] + e4 * Ax[3] + e5 * Ax[4] + e6 * Ax[5] + e7 * Ax[6]);
-    double evy = h * (e1 * Ay[0] + e3 * Ay[2] + e4 * Ay[3] + e5 * Ay[4] + e6 * Ay[5] + e7 * Ay[6]);
-    ex *= fast_rcp(kAtol + fmax(fabs(x), fabs(xn)) * kRtol);
-    ey *= fast_rcp(kAtol + fmax(fabs(y), fabs(yn)) * kRtol);
-    evx *= fast_rcp(kAtol + fmax(fabs(vx), fabs(vxn)) * kRtol);
-    evy *= fast_rcp(kAtol + fmax(fabs(vy), fabs(vyn)) * kRtol);
-    err2 = (ex * ex + ey * ey + evx * evx + evy * evy) * (1.0 / 6.0);  // error_norm ** 2
+    double ex = hh * (HT(eb1) * Ax[0] + HT(eb2) * Ax[1] + HT(eb3) * Ax[2] + HT(eb4) * Ax[3] + HT(eb5) * Ax[4] + HT(eb6) * Ax[5]);
+    double ey = hh * (HT(eb1) * Ay[0] + HT(eb2) * Ay[1] + HT(eb3) * Ay[2] + HT(eb4) * Ay[3] + HT(eb5) * Ay[4] + HT(eb6) * Ay[5]);
+    double evx = h * (HT(e1) * Ax[0] + HT(e3) * Ax[2] + HT(e4) * Ax[3] + HT(e5) * Ax[4] + HT(e6) * Ax[5] + HT(e7) * Ax[6]);
+    double evy = h * (HT(e1) * Ay[0] + HT(e3) * Ay[2] + HT(e4) * Ay[3] + HT(e5) * Ay[4] + HT(e6) * Ay[5] + HT(e7) * Ay[6]);
+    ex *= fast_rcp(HT(atol) + fmax(fabs(x), fabs(xn)) * HT(rtol));
+    ey *= fast_rcp(HT(atol) + fmax(fabs(y), fabs(yn)) * HT(rtol));
+    evx *= fast_rcp(HT(atol) + fmax(fabs(vx), fabs(vxn)) * HT(rtol));
+    evy *= fast_rcp(HT(atol) + fmax(fabs(vy), fabs(vyn)) * HT(rtol));
+    err2 = (ex * ex + ey * ey + evx * evx + evy * evy) * HT(sixth);  // error_norm ** 2
 }
 
 __device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t, inf) - t|, scipy:rk.py:119

@@ -434,6 +434,34 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// ---- -DSG_CHECK_QUEUES: queue invariants, counted on the device (see DevCfg) ----------------------------------------
+#ifdef SG_CHECK_QUEUES
+__device__ __forceinline__ void chk_fail(const DevCfg& c, int k) { atomicAdd(&c.chk_err[k], 1u); }
+__device__ __forceinline__ void chk_visit(const DevCfg& c, long long i) { atomicAdd(&c.chk_visits[i], 1u); }
+__device__ __forceinline__ void chk_slot(const DevCfg& c, bool pushed, uint32_t slot) {
+    if (pushed && (long long)slot >= c.q_cap) chk_fail(c, 1);
+}
+__device__ __forceinline__ void chk_consume(const DevCfg& c, int q, long long i) {
+    if (i < 0 || i >= c.n) {
+        chk_fail(c, 4);
+        return;
+    }
+    if (atomicExch(&c.chk_mark[(size_t)q * (size_t)c.stride + (size_t)i], c.chk_epoch) == c.chk_epoch) chk_fail(c, 3);
+}
+__global__ void chk_pre_kernel(const DevCfg c) {
+    if (threadIdx.x < 11 && threadIdx.x != 4 && threadIdx.x != 5 && c.q_counts[threadIdx.x] != 0) chk_fail(c, 0);
+}
+__global__ void chk_post_kernel(const DevCfg c, uint32_t expected) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += (long long)gridDim.x * blockDim.x)
+        if (c.chk_visits[i] != expected) chk_fail(c, 2);
+    if (blockIdx.x == 0 && threadIdx.x < 11 && threadIdx.x != 4 && threadIdx.x != 5 && c.q_counts[threadIdx.x] != 0)
+        chk_fail(c, 5);
+}
+#define SG_CHK(stmt) stmt
+#else
+#define SG_CHK(stmt)
+#endif
+
 template <class TR>
 __device__ __forceinline__ Act fetch_action(const DevCfg& c, const float* __restrict__ actions, long long i,
                                             unsigned long long step0) {
@@ -491,6 +519,7 @@ __device__ __forceinline__ void finish_env(const DevCfg& c, long long i, EnvRegs
     if (done_out) done_out[i] = (uint8_t)((dn ? 1 : 0) | ((c.pack_flags && trunc) ? 2 : 0));
     if (trunc_out) trunc_out[i] = trunc ? 1 : 0;
     done = dn;
+    SG_CHK(chk_visit(c, i);)
 }
 
 // Post work of a finished env: goal resample (goal.py:155-157) and/or auto-reset (gym.vector 0.21:
@@ -838,6 +867,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     const uint32_t s_cont = (uint32_t)b_both + (uint32_t)__popc(m_cont & below);
     const uint32_t s_event = (uint32_t)(b_both >> 32) + (uint32_t)__popc(m_event & below);
     const uint32_t s_post = queue_push(&c.q_counts[2], need_post);
+    SG_CHK(chk_slot(c, is_cont, s_cont); chk_slot(c, kind == KIND_EVENT, s_event); chk_slot(c, need_post, s_post);)
     if (is_cont) {
         save_cont<TR>(c, c.q_cont, c.scr_cont, s_cont, i, S, lx, ly, kind == KIND_CONT_REJECTED, !publish);
         save_cont_scene<TR>(c, c.scr_cont, s_cont, e, act);
@@ -1104,6 +1134,7 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         double lx = 0, ly = 0;
         if (valid) {
             i = q_in[j];
+            SG_CHK(chk_consume(c, 0, i);)
             EnvRegs<TR> e;
             Act act;
             load_cont_scene<TR>(c, scr_in, j, e, act);  // planets / goal / action terms: coalesced scratch rows, no gather
@@ -1135,6 +1166,7 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         }
         uint32_t s_unused, s_event, s_post;
         queue_push3(&c.q_counts[6], false, &c.q_counts[1], is_event, &c.q_counts[2], need_post, s_unused, s_event, s_post);
+        SG_CHK(chk_slot(c, is_event, s_event); chk_slot(c, need_post, s_post);)
         if (is_event) {
             Integ<TR> So;
             So.x = io.x; So.y = io.y; So.th = io.th; So.vx = io.vx; So.vy = io.vy; So.om = io.om; So.t = io.t_old;
@@ -1186,6 +1218,7 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
             for (int k = 0; k < 3; ++k) cp_async8(&s_tail[k][threadIdx.x], p + (22 + k) * cap);
             cp_async_commit();
             const long long i = c.q_event[j];
+            SG_CHK(chk_consume(c, 1, i);)
             EnvRegs<TR> e;
             load_env<TR>(c, i, e);
             const Act act = fetch_action<TR>(c, actions, i, step0);
@@ -1227,6 +1260,7 @@ tail_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
         } else if (j < total) {
             const uint32_t w = c.q_post[j - n_event];
             post_i = (long long)(w & kPostIndex);
+            SG_CHK(chk_consume(c, 2, post_i);)
             post_reached = (w & kPostReached) != 0;
             post_done = (w & kPostDone) != 0;
             do_post = true;
@@ -1291,6 +1325,7 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
             if (mine) {
                 const double* p = c.scr_event + j;
                 i = c.q_event[j];
+                SG_CHK(chk_consume(c, 1, i);)
                 d.x0 = p[0 * cap]; d.y0 = p[1 * cap]; d.th0 = p[2 * cap]; d.vx0 = p[3 * cap]; d.vy0 = p[4 * cap];
                 d.om0 = p[5 * cap]; d.h = p[6 * cap]; d.t_old = p[7 * cap];
 #pragma unroll
@@ -1344,6 +1379,7 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
                 if (reward) reward[i] = r;
                 if (done_out) done_out[i] = 1;
                 if (trunc_out) trunc_out[i] = 0;
+                SG_CHK(chk_visit(c, i);)
                 if (!c.auto_reset) {
                     store_ship<TR>(c, i, e);
                     c.elapsed[i] = elapsed;
@@ -1374,6 +1410,7 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
             } else if (j < total) {
                 const uint32_t w = c.q_post[j - n_event];
                 i = (long long)(w & kPostIndex);
+                SG_CHK(chk_consume(c, 2, i);)
                 const bool reached = (w & kPostReached) != 0, done = (w & kPostDone) != 0;
                 do_reset = done && c.auto_reset;
                 do_goal = TR::TASK == TASK_GOAL && reached && !do_reset;
@@ -1555,6 +1592,8 @@ struct sg_env {
     bool owns_state;
     double* d_stats;
     void* d_queues;  // work queues + scratch of the split step path
+    uint32_t* d_chk;  // -DSG_CHECK_QUEUES: error counters [8] | visits [N] | marks [3][N]
+    uint32_t chk_steps;
     size_t q_bytes_total;
     // split path: the envs are processed as `n_sub` independent sub-batches on internal streams, so that
     // the latency-bound continuation / tail kernels of one sub-batch overlap the hot kernel of another;
@@ -1844,6 +1883,7 @@ static void build_dev(sg_env* h) {
         d.r0 = c.kepler_planet_radius;
         d.r1 = c.kepler_border_radius;
     }
+    d.gmm = d.gm0 * d.inv_mass;
     d.survival = c.survival_reward_scale;
     d.goal_vel = c.goal_vel_reward_scale;
     d.safety = c.safety_reward_scale;
@@ -1895,6 +1935,12 @@ static void build_dev(sg_env* h) {
         x.scr_event = x.scr_cont + (size_t)kContFields * n;
         x.scr_cont2 = x.scr_event + (size_t)kEventFields * n;
         x.q_cap = sb.n;
+#ifdef SG_CHECK_QUEUES
+        x.chk_err = h->d_chk;
+        x.chk_visits = h->d_chk ? h->d_chk + 8 + sb.off : nullptr;
+        x.chk_mark = h->d_chk ? h->d_chk + 8 + h->n + sb.off : nullptr;  // [3][stride], stride = envs of the handle
+        x.chk_epoch = 0;
+#endif
         q += queue_bytes(sb.n);
     }
     h->dev.q_counts = h->sub[0].dev.q_counts;
@@ -1922,6 +1968,8 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
     h->step_count = 0;
     h->launches = 0;
     h->d_queues = nullptr;
+    h->d_chk = nullptr;
+    h->chk_steps = 0;
     h->d_stats = nullptr;
     h->n_sub = 1;
     h->n_graphs = 0;
@@ -1976,6 +2024,11 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
         }
         if (err == cudaSuccess) err = cudaMalloc(&h->d_queues, q_bytes);
         if (err == cudaSuccess) err = cudaMemset(h->d_queues, 0, q_bytes);
+#ifdef SG_CHECK_QUEUES
+        const size_t chk_bytes = (8 + 4 * (size_t)n_envs) * sizeof(uint32_t);
+        if (err == cudaSuccess) err = cudaMalloc((void**)&h->d_chk, chk_bytes);
+        if (err == cudaSuccess) err = cudaMemset(h->d_chk, 0, chk_bytes);
+#endif
         h->q_bytes_total = q_bytes;
         for (int s = 0; s < h->n_sub && err == cudaSuccess && h->n_sub > 1; ++s) {
             err = cudaStreamCreateWithFlags(&h->sub[s].stream, cudaStreamNonBlocking);
@@ -2002,7 +2055,7 @@ extern "C" int sg_create(const sg_config* cfg, int64_t n_envs, int device, uint6
         const char* env_tail = getenv("SG_TAIL");
         h->tail_mode = env_tail ? atoi(env_tail) : 2;
         const char* env_tg = getenv("SG_TAIL_CTAS");
-        h->tail_grid = (env_tg && atoi(env_tg) > 0) ? atoi(env_tg) : 2;
+        h->tail_grid = (env_tg && atoi(env_tg) > 0) ? atoi(env_tg) : 1;  // measured 1 / 2 / 4: 5.72 / 5.67 / 5.43e9
         const char* env_pri = getenv("SG_PRIORITY");
         h->use_priority = env_pri ? atoi(env_pri) : 0;
         if (err == cudaSuccess) {
@@ -2044,6 +2097,7 @@ extern "C" void sg_destroy(sg_env* h) {
     if (h->owns_state && h->state) cudaFree(h->state);
     if (h->d_stats) cudaFree(h->d_stats);
     if (h->d_queues) cudaFree(h->d_queues);
+    if (h->d_chk) cudaFree(h->d_chk);
     for (int g = 0; g < h->n_graphs; ++g)
         if (h->graphs[g].exec) cudaGraphExecDestroy(h->graphs[g].exec);
     for (int s = 0; s < 8; ++s) {
@@ -2107,6 +2161,25 @@ extern "C" int sg_reseed(sg_env* h, uint64_t seed) {
     sync_step_counters(h, nullptr);
     SG_CUDA(h, cudaDeviceSynchronize());
     return SG_OK;
+}
+
+// -DSG_CHECK_QUEUES builds: the device-side invariant counters of the split step's work queues (DevCfg::chk_err),
+// out[0..5] = violations by kind, out[6] = env steps checked.  Other builds: SG_ERR_INVALID ("not compiled in").
+extern "C" int sg_debug_queue_check(sg_env* h, uint64_t out[8]) {
+    if (!h || !out) return SG_ERR_INVALID;
+#ifdef SG_CHECK_QUEUES
+    SG_CUDA(h, cudaSetDevice(h->device));
+    SG_CUDA(h, cudaDeviceSynchronize());
+    uint32_t e[8];
+    SG_CUDA(h, cudaMemcpy(e, h->d_chk, sizeof(e), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) out[k] = e[k];
+    out[6] = h->chk_steps;
+    out[7] = 1;
+    return SG_OK;
+#else
+    for (int k = 0; k < 8; ++k) out[k] = 0;
+    return fail(h, SG_ERR_INVALID, "sg_debug_queue_check: this build was compiled without -DSG_CHECK_QUEUES");
+#endif
 }
 
 // debugging aid (SG_TIMING=1): mean milliseconds of {hot, continuation, tail} per env step so far
@@ -2186,6 +2259,10 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         uint8_t* dn = a.done ? a.done + off : nullptr;
         uint8_t* tr = a.trunc ? a.trunc + off : nullptr;
         sg_env* hm = const_cast<sg_env*>(h);
+#ifdef SG_CHECK_QUEUES
+        dv.chk_epoch = h->chk_steps + 1;
+        chk_pre_kernel<<<1, 32, 0, a.stream>>>(dv);
+#endif
         if (h->timing) cudaEventRecord(h->tev[0], a.stream);
         if (h->use_fused) {
             int fused_blocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
@@ -2236,6 +2313,9 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
             launch_k(tail2_kernel<TR, OT>, tail2_blocks, kTail2Block, small, h->use_pdl != 0 && !h->timing, dv, act, obs,
                      rew, dn, tr);
         }
+#ifdef SG_CHECK_QUEUES
+        chk_post_kernel<<<sms, 256, 0, small>>>(dv, h->chk_steps + 1);
+#endif
         if (h->timing) {  // debugging aid: synchronous, never on in benchmarks
             cudaEventRecord(h->tev[3], small);
             cudaEventSynchronize(h->tev[3]);
@@ -2468,6 +2548,7 @@ static int step_impl(sg_env* h, const float* d_actions, int K, void* d_obs, int 
         int rc = launch_split_step(h, stream, a, K == 1);
         if (rc != SG_OK) return rc;
         h->step_count += 1;  // the tail kernels advance the device-side counters
+        h->chk_steps += 1;
     }
     return SG_OK;
 }

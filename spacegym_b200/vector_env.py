@@ -250,12 +250,23 @@ class BatchedSpaceEnv:
         return self._host_buffers()[1]["act"]
 
     def step_async(self, actions=None, check_actions=None, want_obs=True):
-        """Upload `actions` (numpy [N, 2] float32, or [N] ints for discrete envs; None = already written to
-        `action_buffer`), step, and start downloading the result block on the handle's own stream (ordered after
+        """Upload `actions` (numpy [N, 2] float32, or [N] ints for discrete envs; a pinned float32 CPU torch tensor
+        is uploaded in place; None = already written to `action_buffer`), step, and start downloading the result block on the handle's own stream (ordered after
         the work already enqueued on the current torch stream).  want_obs=False leaves the observation on the
         device (9 bytes per env come back instead of 9 + 4 D)."""
         hb, hn = self._host_buffers()
-        if actions is not None:
+        act_ptr = self._ptr(hb["act"])
+        if isinstance(actions, torch.Tensor):
+            # a pinned float32 [N, 2] CPU tensor is uploaded from where it is (no staging copy); the caller keeps it
+            # unchanged until step_wait() returns
+            if not (actions.device.type == "cpu" and actions.is_pinned() and actions.dtype == torch.float32
+                    and actions.is_contiguous() and tuple(actions.shape) == (self.num_envs, 2)):
+                raise ValueError("step_async(torch tensor): expected a pinned contiguous float32 CPU tensor of shape "
+                                 f"{(self.num_envs, 2)} (CUDA tensors go through step())")
+            if self.check_actions if check_actions is None else check_actions:
+                self._assert_actions(actions, True)
+            act_ptr = self._ptr(actions)
+        elif actions is not None:
             a = np.asarray(actions)
             if self.check_actions if check_actions is None else check_actions:
                 self._assert_actions(a, False)
@@ -266,7 +277,7 @@ class BatchedSpaceEnv:
                 assert a.shape == (self.num_envs, 2), f"expected actions of shape {(self.num_envs, 2)}, got {a.shape}"
                 np.copyto(hn["act"], a, casting="same_kind")
         self._host_want_obs = bool(want_obs)
-        check(self._L.sg_step_host_block_async(self._h, self._ptr(hb["act"]), self._ptr(hb["block"]),
+        check(self._L.sg_step_host_block_async(self._h, act_ptr, self._ptr(hb["block"]),
                                                1 if hb["f32"] else 0, 1 if want_obs else 0, self._stream()), self._h)
 
     def step_wait(self):

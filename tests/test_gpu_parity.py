@@ -54,6 +54,19 @@ LOCKSTEP = [(c, "split") for c in ("goal2p", "goal3p", "goal4p", "goal3p_accel",
 LOCKSTEP += [(c, "fused") for c in ("goal3p", "goal2p", "kepler_hard_accel_rand", "goal3p_discrete", "donotcrash")]
 
 
+def _assert_boundary_ties(oracle, cfg, prev_envs, actions, bad_idx):
+    """Every env-step on which the engine and the oracle parted must sit on a decision boundary: the oracle's
+    margin (min distance of an accept/reject, event-sign, h0-branch or goal-reached decision from its threshold,
+    oracle/sg_oracle.h so_step_diag.margin) is at rounding level there.  Anything else is a bug, not a tie."""
+    P = int(cfg.n_planets)
+    for k in bad_idx:
+        e = prev_envs[k]
+        planets = np.array(e["planets"][:2 * max(P, 1)]).reshape(-1, 2)
+        orbit = (float(e["orbit_angle"]), float(e["orbit_ecc"]), float(cfg.ref_orbit_a))
+        r = oracle.step_transition(cfg, np.array(e["y"]), planets, np.array(e["goal"]), orbit, actions[k])
+        assert r["margin"] < 1e-12, f"env {k} diverged away from any decision boundary (margin {r['margin']:.3e})"
+
+
 @pytest.mark.parametrize("case,mode", LOCKSTEP)
 def test_rollout_lockstep_with_oracle_engine(oracle, case, mode):
     """Whole engine (auto-reset, TimeLimit, Philox streams, goal resampling) in lockstep with the CPU twin,
@@ -67,22 +80,43 @@ def test_rollout_lockstep_with_oracle_engine(oracle, case, mode):
     obs_d = env.reset()
     assert close(obs_d.cpu().numpy(), obs_o).all()
     assert compare_engine_to_oracle(cfg, env.get_state(), eng.envs).all()
-    rng = np.random.RandomState(5)
+    diverged = _lockstep(oracle, cfg, eng, env, n, T, np.random.RandomState(5))
+    assert diverged <= 2, f"{diverged} env-steps diverged out of {n * T}"
+    so, sd = eng.stats, env.stats()
+    assert abs(sd["episodes"] - so[2]) <= 2 and sd["episodes"] > n
+    env.close()
+
+
+def _lockstep(oracle, cfg, eng, env, n, T, rng):
+    """T env steps of the engine and the oracle twin from the same actions; returns the number of env-steps on
+    which they parted, each of them proven to be a boundary tie (then the engine is re-synchronised)."""
     diverged = 0
     for t in range(T):
         a = random_actions(rng, 1, n, bool(cfg.discrete))
+        prev = eng.envs.copy()
         o_o, r_o, d_o, tr_o = eng.step(a)
         o_d, r_d, d_d, info = env.step(to_dev(a[0]))
         ok = close(o_d.cpu().numpy(), o_o).all(axis=1) & close(r_d.cpu().numpy(), r_o[0])
         ok &= (d_d.cpu().numpy() == d_o[0].astype(bool)) & (info["TimeLimit.truncated"].cpu().numpy() == tr_o[0].astype(bool))
         ok &= compare_engine_to_oracle(cfg, env.get_state(), eng.envs)
-        bad = int((~ok).sum())
-        if bad:  # boundary ties can flip a discrete decision: count, then re-synchronise from the oracle
-            diverged += bad
+        bad = np.flatnonzero(~ok)
+        if len(bad):  # boundary ties can flip a discrete decision: prove it, count, re-synchronise from the oracle
+            _assert_boundary_ties(oracle, cfg, prev, a[0], bad)
+            diverged += len(bad)
             env.set_state(oracle_state_to_engine(cfg, eng.envs))
-    assert diverged <= 2, f"{diverged} env-steps diverged out of {n * T}"
-    so, sd = eng.stats, env.stats()
-    assert abs(sd["episodes"] - so[2]) <= 2 and sd["episodes"] > n
+    return diverged
+
+
+def test_config2_kepler_circle_4096_envs_lockstep(oracle):
+    """BASELINE configs[1] / SURVEY §8d-2 verbatim: KeplerCircleOrbit-v0, 4096 envs, 64 steps in lockstep with the
+    oracle twin from identical actions (state / observation / reward to 1e-9 max(1, |ref|), done exact)."""
+    n, T, seed = 4096, 64, 0
+    cfg = oracle.config_from_id("KeplerCircleOrbit-v0")
+    eng = oracle.Engine(cfg, n, seed=seed)
+    env = sg.make("KeplerCircleOrbit-v0", n, seed=seed)
+    assert close(env.reset().cpu().numpy(), eng.reset()).all()
+    diverged = _lockstep(oracle, cfg, eng, env, n, T, np.random.RandomState(2))
+    assert diverged <= 1, f"{diverged} env-steps diverged out of {n * T}"
     env.close()
 
 
@@ -141,8 +175,11 @@ def test_shard_invariance():
         e.close()
 
 
-def test_host_buffer_path_matches_device_path():
-    a = sg.make("GoalContinuous3P-v0", 1000, seed=11)
+@pytest.mark.parametrize("host_dtype", ["float32", "float64"])
+def test_host_buffer_path_matches_device_path(host_dtype):
+    """step(numpy) (packed host result block, one copy each way) == step(torch) on a twin handle: rewards and flags
+    exact, observations exact (float64 block) or the float32 rounding of the device path's rows."""
+    a = sg.make("GoalContinuous3P-v0", 1000, seed=11, host_obs_dtype=host_dtype)
     b = sg.make("GoalContinuous3P-v0", 1000, seed=11)
     a.reset(); b.reset()
     rng = np.random.RandomState(0)
@@ -150,9 +187,45 @@ def test_host_buffer_path_matches_device_path():
         act = rng.uniform(-1, 1, size=(1000, 2)).astype(np.float32)
         oh, rh, dh, ih = a.step(act)
         od, rd, dd, idv = b.step(to_dev(act))
-        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy())
+        want = od.cpu().numpy()
+        assert oh.dtype == np.dtype(host_dtype)
+        assert np.array_equal(oh, want.astype(host_dtype)) and np.array_equal(rh, rd.cpu().numpy())
         assert np.array_equal(dh, dd.cpu().numpy())
+        assert np.array_equal(ih["TimeLimit.truncated"], idv["TimeLimit.truncated"].cpu().numpy())
     a.close(); b.close()
+
+
+def test_host_path_is_ordered_after_the_callers_stream(oracle):
+    """reset(); step(numpy) and mixed step(torch) / step(numpy) on one handle.  The host path runs on the
+    handle's own non-blocking stream; it must start after the reset / device-path step enqueued on the caller's stream
+    and the next device-path call must see its results.  Checked against the oracle twin transition by transition."""
+    n, seed = 4096, 5
+    env = sg.make("GoalContinuous3P-v0", n, seed=seed, host_obs_dtype="float64", max_episode_steps=40)
+    cfg = oracle.config_from_id("GoalContinuous3P-v0", max_episode_steps=40)
+    rng = np.random.RandomState(1)
+    for rep in range(3):
+        # env.seed(s); env.reset() replays what a fresh handle with seed s does (spaceship_env.py:92-94): the twin is new
+        assert env.seed(seed + rep) == [seed + rep]
+        twin = oracle.Engine(cfg, n, seed=seed + rep)
+        od, oo = env.reset(), twin.reset()   # reset on the torch stream, host step right behind it
+        assert close(od.cpu().numpy(), oo).all()
+        for k in range(12):
+            act = rng.uniform(-1, 1, size=(n, 2)).astype(np.float32)
+            oo, ro, do, _ = twin.step(act[None])
+            if (k + rep) % 3 == 0:
+                o, r, d, _ = env.step(to_dev(act))
+                o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+            else:
+                o, r, d, _ = env.step(act)
+            ok = close(o, oo).all(axis=1) & close(r, ro[0]) & (d == do[0].astype(bool))
+            assert (~ok).sum() == 0, f"rep {rep} step {k}: {(~ok).sum()} envs differ"
+    # want_obs=False: reward | flags only, the observation stays on the device
+    act = rng.uniform(-1, 1, size=(n, 2)).astype(np.float32)
+    oo, ro, do, _ = twin.step(act[None])
+    env.step_async(act, want_obs=False)
+    o, r, d, _ = env.step_wait()
+    assert o is None and close(r, ro[0]).all() and (d == do[0].astype(bool)).all()
+    env.close()
 
 
 def test_float32_observation_mode():
@@ -230,7 +303,7 @@ def test_reset_distribution_matches_reference(case):
     env.close()
 
 
-def test_full_size_rollout_properties():
+def test_full_size_rollout_properties(oracle):
     """BASELINE config 3 size: GoalContinuous3P-v0, 262144 envs, auto-reset. Size-independent checks."""
     n = 262144
     env = sg.make("GoalContinuous3P-v0", n, seed=7)
@@ -256,6 +329,9 @@ def test_full_size_rollout_properties():
     assert abs(s["length_sum"] + float(st["elapsed"].sum()) - 200.0 * n) < 0.5  # every env step is accounted for
     frac = total_done / (200.0 * n)
     assert 0.01 < frac < 0.04  # ~2 % of random-policy steps end an episode
+    # the benchmark configuration at its full size against the oracle: 1500 random transitions of the next step
+    cfg = oracle.config_from_id("GoalContinuous3P-v0")
+    assert _spot_check_against_oracle(oracle, "goal", env, cfg, 1500, np.random.RandomState(3)) == 0
     env.close()
 
 
