@@ -69,6 +69,7 @@ enum sg_status {
 #define SG_ENV_BRENT_SIGN 2u     /* reference: brentq would raise ValueError */
 #define SG_ENV_FREE_OVERFLOW 4u  /* free-tile multiset longer than 64 entries */
 #define SG_ENV_NONFINITE 8u
+#define SG_ENV_PLACEMENT 16u     /* one-planet GoalEnv: no room in the sampled direction (reference: assert, goal.py:96) */
 
 /* Same names and meaning as the reference constructor kwargs. */
 typedef struct sg_config {

@@ -63,6 +63,15 @@ void so_config_finalize(so_config* cfg) {
         cfg->world_size = 3.0;
         cfg->step_size = 0.07;
         cfg->max_abs_vel_angle = 6.0;
+        if (P == 1) { /* goal.py:79-82 (_init_one_planet): no tiling */
+            cfg->rows = cfg->cols = 0;
+            cfg->hex_a = cfg->hex_height = cfg->hex_width = cfg->tiling_width = 0;
+            cfg->planet_radius[0] = 0.8;
+            cfg->planet_mass[0] = 1e9;
+            cfg->goal_radius = 0.2;
+            cfg->ship_radius = 0.2;
+            return;
+        }
         tiling_rows_cols_a(min_tiles, cfg->world_size, &r, &c, &a);
         cfg->rows = r;
         cfg->cols = c;
@@ -788,8 +797,40 @@ static void tile_center(const so_config* cfg, const so_env* env, int tile, doubl
     }
 }
 
-/* hexagonal_tiling.py:95-128 */
+/* helpers.py:38-46 (get_max_dist_in_direction): the positive candidates' minimum; IEEE division like NumPy's */
+static double max_dist_in_direction(double max_pos, const double obj[2], const double unit[2]) {
+    double cand[4] = {(max_pos - obj[0]) / unit[0], (-max_pos - obj[0]) / unit[0], (max_pos - obj[1]) / unit[1],
+                      (-max_pos - obj[1]) / unit[1]};
+    double best = INFINITY;
+    int any = 0;
+    for (int i = 0; i < 4; ++i)
+        if (cand[i] > 0) {
+            if (!any || cand[i] < best) best = cand[i];
+            any = 1;
+        }
+    return best;
+}
+
+/* goal.py:90-99 (_sample_position_outside_one_planet) */
+static void sample_outside_one_planet(const so_config* cfg, so_env* env, so_draws* d, const double planet[2],
+                                      double clearance, double out[2]) {
+    double max_obj_pos = cfg->world_size / 2 - clearance;
+    double ang = 0 + (SO_TWO_PI - 0) * so_next_uniform(d);
+    double unit[2] = {cos(ang), sin(ang)};
+    double dmax = max_dist_in_direction(max_obj_pos, planet, unit);
+    double dmin = cfg->planet_radius[0] + clearance;
+    if (!(dmin < dmax)) env->status |= SO_ERR_PLACEMENT; /* the reference asserts here */
+    double dist = dmin + (dmax - dmin) * so_next_uniform(d);
+    out[0] = planet[0] + unit[0] * dist;
+    out[1] = planet[1] + unit[1] * dist;
+}
+
+/* hexagonal_tiling.py:95-128; one planet: goal.py:122-123 */
 void so_find_new_goal(const so_config* cfg, so_env* env, so_draws* d) {
+    if (cfg->n_planets == 1) {
+        sample_outside_one_planet(cfg, env, d, env->planets, cfg->goal_radius, env->goal);
+        return;
+    }
     if (env->goal_tile >= 0) {
         if (env->n_free < SO_MAX_FREE) env->free_tiles[env->n_free++] = env->ship_tile;
         else env->status |= SO_ERR_FREE_OVERFLOW;
@@ -825,7 +866,40 @@ void so_find_new_goal(const so_config* cfg, so_env* env, so_draws* d) {
     env->goal[1] = cpos[1] + rr * sin(ang);
 }
 
+/* GoalEnv with n_planets = 1 (goal.py:79-82,90-123,133-145).  Upstream this configuration cannot run: `_reset`
+ * unpacks (ship, goal, planet) as (ship, *planets) and so puts the planet on the sampled GOAL position, and
+ * `_reward` dereferences `self._hexagonal_tiling._debug` on None.  Semantics chosen here ("the obvious
+ * fix"), pinned by goldens generated from the reference with exactly these two lines patched
+ * (tests/golden/make_golden.py, class GoalOnePlanet): the planet takes the sampled planet position (the first goal
+ * sample is drawn and discarded: `_resample_goal` right after draws the goal the episode starts with), and the
+ * goal-reached threshold is goal_radius. */
+static void reset_goal_one_planet(const so_config* cfg, so_env* env, so_draws* d) {
+    double max_pos = cfg->world_size / 2 - cfg->planet_radius[0];
+    double clear = fmax(cfg->ship_radius, cfg->goal_radius);
+    double pdist = 0 + ((max_pos - 2 * clear) - 0) * so_next_uniform(d);
+    double pang = 0 + (SO_TWO_PI - 0) * so_next_uniform(d);
+    env->planets[0] = cos(pang) * pdist;
+    env->planets[1] = sin(pang) * pdist;
+    double ship[2], unused_goal[2];
+    sample_outside_one_planet(cfg, env, d, env->planets, cfg->ship_radius, ship);
+    sample_outside_one_planet(cfg, env, d, env->planets, cfg->goal_radius, unused_goal);
+    env->y[0] = ship[0];
+    env->y[1] = ship[1];
+    env->goal_tile = -1;
+    so_find_new_goal(cfg, env, d); /* goal.py:138 */
+    env->y[2] = 0 + (SO_TWO_PI - 0) * so_next_uniform(d);
+    env->y[3] = so_next_normal(d) * 0.07;
+    env->y[4] = so_next_normal(d) * 0.07;
+    double maxw = 0.7 * cfg->max_abs_vel_angle;
+    double w = so_next_normal(d) * maxw / 3;
+    env->y[5] = fmin(fmax(w, -maxw), maxw);
+}
+
 static void reset_goal_env(const so_config* cfg, so_env* env, so_draws* d) {
+    if (cfg->n_planets == 1) {
+        reset_goal_one_planet(cfg, env, d);
+        return;
+    }
     /* HexagonalTiling.reset, hexagonal_tiling.py:53-93 */
     int P = cfg->n_planets, n_tiles = cfg->rows * cfg->cols;
     env->goal_tile = -1;

@@ -81,6 +81,7 @@ typedef struct so_step_diag {
 #define SO_ERR_BRENT_SIGN 2
 #define SO_ERR_FREE_OVERFLOW 4
 #define SO_ERR_NONFINITE 8
+#define SO_ERR_PLACEMENT 16 /* one-planet GoalEnv: no room in the sampled direction (the reference asserts, goal.py:96) */
 
 /* draw source for resets: either a tape (pinning against the reference) or Philox */
 typedef struct so_draws {

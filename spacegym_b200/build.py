@@ -3,7 +3,7 @@
     python -m spacegym_b200.build [--force] [-v] [--single]
 
 The engine is one source file (csrc/sg_engine.cu) whose kernels are templated over the env family; it is compiled
-as five translation units in parallel (-DSG_PART=0..4: C ABI + Goal 2P | Goal 3P | Goal 4P | Kepler | DoNotCrash)
+as six translation units in parallel (-DSG_PART=0..5: C ABI + Goal 2P | Goal 3P | Goal 4P | Kepler | DoNotCrash | Goal 1P)
 and linked, ~1.5 min on 8 cores instead of 4.5 min for the single unit (`--single`, same code).
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the tree.
 """
@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", f) for f in ("sg_engine.cu", "sg_device.cuh", "sg_tail.cuh")] + [
     os.path.join(ROOT, "include", "spacegym_b200.h")]
 OUT = os.path.join(HERE, "libspacegym_b200.so")
-N_PARTS = 5
+N_PARTS = 6
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -337,6 +337,7 @@ struct Traits {
     static constexpr int DISC = DISC_;
     static constexpr int NEV = (TASK_ == TASK_GOAL ? NP_ : 2) + 3;   // events (dynamic_model.py:183-217)
     static constexpr int D = TASK_ == TASK_GOAL ? 9 + 2 * NP_ : (TASK_ == TASK_KEPLER ? 10 : 7);  // observation length
+    static constexpr bool TILED = TASK_ == TASK_GOAL && NP_ > 1;    // hexagonal-tiling placement (one planet: goal.py:90-123)
 };
 
 template <class TR>
@@ -1335,6 +1336,55 @@ __device__ inline void choice_no_replace(Rng& rng, int n, int k, int (&out)[KMAX
     }
 }
 
+// GoalEnv._sample_position_outside_one_planet (goal.py:90-99) with helpers.get_max_dist_in_direction (helpers.py:38-46):
+// a point on a uniformly drawn ray from the planet, between planet_radius + clearance and the world box shrunk by
+// the clearance.  IEEE divisions as in NumPy (a zero direction component gives +-inf / nan candidates, which the
+// `> 0` filter treats as the reference's does).  Works on either draw session (Rng / Draws).
+template <class RNG>
+__device__ inline void sample_outside_one_planet(const DevCfg& c, RNG& rng, double px, double py, double clearance,
+                                                 double& ox, double& oy, uint32_t& status) {
+    const double max_obj = c.half_ws - clearance;
+    const double ang = kTwoPi * rng.uniform();
+    double sn, cs;
+    sincos_cold(ang, &sn, &cs);
+    const double cand[4] = {(max_obj - px) / cs, (-max_obj - px) / cs, (max_obj - py) / sn, (-max_obj - py) / sn};
+    double dmax = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (cand[k] > 0 && cand[k] < dmax) dmax = cand[k];
+    const double dmin = c.r0 + clearance;
+    if (!(dmin < dmax)) status |= 16u;  // SG_ENV_PLACEMENT: the reference asserts (goal.py:96)
+    const double dist = dmin + (dmax - dmin) * rng.uniform();
+    ox = px + cs * dist;
+    oy = py + sn * dist;
+}
+
+// env.reset of the one-planet GoalEnv (goal.py:101-109,133-145 with the unpacking of :134 fixed: the planet takes
+// the sampled planet position, the first goal sample is drawn and dropped, `_resample_goal` draws the goal).
+// out: x, y, th, vx, vy, om | planet (x, y) | goal (x, y)
+template <class RNG>
+__device__ inline void reset_goal_one_planet(const DevCfg& c, RNG& rng, double* out, uint32_t& status) {
+    const double max_pos = c.half_ws - c.r0;
+    const double clear = fmax(c.ship_radius, c.goal_radius);
+    const double pdist = (max_pos - 2 * clear) * rng.uniform();
+    const double pang = kTwoPi * rng.uniform();
+    double sn, cs;
+    sincos_cold(pang, &sn, &cs);
+    const double px = cs * pdist, py = sn * pdist;
+    out[6] = px;
+    out[7] = py;
+    double ux, uy;
+    sample_outside_one_planet(c, rng, px, py, c.ship_radius, out[0], out[1], status);
+    sample_outside_one_planet(c, rng, px, py, c.goal_radius, ux, uy, status);
+    sample_outside_one_planet(c, rng, px, py, c.goal_radius, out[8], out[9], status);
+    out[2] = kTwoPi * rng.uniform();
+    out[3] = rng.normal() * 0.07;
+    out[4] = rng.normal() * 0.07;
+    const double maxw = 0.7 * c.om_max;
+    const double w = rng.normal() * maxw / 3;
+    out[5] = fmin(fmax(w, -maxw), maxw);
+}
+
 // HexagonalTiling.find_new_goal (hexagonal_tiling.py:95-134)
 static __device__ __noinline__ void find_new_goal(const DevCfg& c, Tiles& t, Rng& rng, double& gx, double& gy, uint32_t& status) {
     if (t.goal_tile != 63u) {
@@ -1384,6 +1434,10 @@ static __device__ __noinline__ void find_new_goal(const DevCfg& c, Tiles& t, Rng
 // Goal resample on a reached goal (goal.py:155-157): cold, touches the tile state in HBM.
 template <class TR>
 static __device__ __noinline__ void resample_goal(const DevCfg& c, long long i, Rng* rng, double* gxy, uint32_t* status) {
+    if (!TR::TILED) {  // one planet: goal.py:122-123
+        sample_outside_one_planet(c, *rng, c.planets[i], c.planets[c.stride + i], c.goal_radius, gxy[0], gxy[1], *status);
+        return;
+    }
     Tiles t;
     load_tiles(c, i, t);
     find_new_goal(c, t, *rng, gxy[0], gxy[1], *status);
@@ -1396,7 +1450,9 @@ static __device__ __noinline__ void resample_goal(const DevCfg& c, long long i, 
 template <class TR>
 static __device__ __noinline__ void reset_env(const DevCfg& c, long long i, Rng* rngp, double* out, uint32_t* status) {
     Rng& rng = *rngp;
-    if (TR::TASK == TASK_GOAL) {
+    if (TR::TASK == TASK_GOAL && !TR::TILED) {
+        reset_goal_one_planet(c, rng, out, *status);
+    } else if (TR::TASK == TASK_GOAL) {
         constexpr int P = TR::NP;
         const int n_tiles = c.rows * c.cols;
         Tiles t;

@@ -27,9 +27,9 @@
 #include "sg_device.cuh"
 #include "sg_tail.cuh"
 
-// SG_PART: the library can be built as five translation units compiled in parallel (spacegym_b200/build.py):
-// part 0 = C ABI + dispatch + the 2-planet GoalEnv kernels, parts 1-4 = the kernels of one more env family each
-// (Goal 3P, Goal 4P, Kepler, DoNotCrash).  Without SG_PART the whole engine is one translation unit.
+// SG_PART: the library can be built as six translation units compiled in parallel (spacegym_b200/build.py):
+// part 0 = C ABI + dispatch + the 2-planet GoalEnv kernels, parts 1-5 = the kernels of one more env family each
+// (Goal 3P, Goal 4P, Kepler, DoNotCrash, Goal 1P).  Without SG_PART the whole engine is one translation unit.
 #if defined(SG_PART) && SG_PART != 0
 #define SG_MAIN_PART 0
 #else
@@ -1420,7 +1420,7 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
             Tiles t;
             if (work) {
                 ctr = c.rng_ctr[i];
-                if (do_goal) load_tiles(c, i, t);
+                if (do_goal && TR::TILED) load_tiles(c, i, t);
             }
             if (__any_sync(0xffffffffu, work)) {
                 if (work) philox_fill<draw_blocks<TR>()>(c.seed, (unsigned long long)(c.first_env + i), ctr, s_u + lane);
@@ -1431,7 +1431,10 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
             double out[8 + 2 * TR::NP];
             double gx = 0, gy = 0;
             if (do_reset) reset_env_t<TR>(c, rng, out, t, status);
-            if (do_goal) find_new_goal_t<TR::NP>(c, t, rng, gx, gy, status);
+            if (do_goal) {
+                if (TR::TILED) find_new_goal_t<TR::NP>(c, t, rng, gx, gy, status);
+                else sample_outside_one_planet(c, rng, c.planets[i], c.planets[c.stride + i], c.goal_radius, gx, gy, status);
+            }
             bar_sync(1, kTail2Block);  // E has read what it needs of these envs
             if (do_reset) {
                 EnvRegs<TR> e;
@@ -1445,7 +1448,7 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
                 adopt_reset<TR>(c, e, out);
                 store_ship<TR>(c, i, e);
                 if (TR::TASK == TASK_GOAL || (TR::TASK == TASK_KEPLER && c.randomize)) store_scene<TR>(c, i, e, true);
-                if (TR::TASK == TASK_GOAL) store_tiles(c, i, t, true);
+                if (TR::TILED) store_tiles(c, i, t, true);
                 c.elapsed[i] = 0;
                 c.ep_return[i] = 0.0;
                 if (obs) {
@@ -1460,7 +1463,7 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
             if (do_goal) {
                 c.goal[i] = gx;
                 c.goal[c.stride + i] = gy;
-                store_tiles(c, i, t, false);
+                if (TR::TILED) store_tiles(c, i, t, false);
             }
             if (work) c.rng_ctr[i] = ctr + rng.blocks_used();
             if (status) atomicOr(&c.status[i], status);
@@ -1484,8 +1487,11 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
 }
 
 #if SG_MAIN_PART
-__global__ void set_step_counter_kernel(uint32_t* q_counts, unsigned long long value) {
-    *reinterpret_cast<unsigned long long*>(q_counts + 4) = value;
+struct StepCounterPtrs {
+    uint32_t* q[8];
+};
+__global__ void set_step_counter_kernel(StepCounterPtrs p, int n_sub, unsigned long long value) {
+    if ((int)threadIdx.x < n_sub) *reinterpret_cast<unsigned long long*>(p.q[threadIdx.x] + 4) = value;
 }
 #endif
 
@@ -1511,7 +1517,7 @@ reset_kernel(const DevCfg c, const uint8_t* __restrict__ mask, OT* __restrict__ 
         adopt_reset<TR>(c, e, out);
         store_ship<TR>(c, i, e);
         store_scene<TR>(c, i, e, true);
-        if (TR::TASK == TASK_GOAL) store_tiles(c, i, t, true);
+        if (TR::TILED) store_tiles(c, i, t, true);
         c.elapsed[i] = 0;
         c.ep_return[i] = 0.0;
         c.rng_ctr[i] = ctr + rng.blocks_used();
@@ -1686,7 +1692,18 @@ extern "C" int sg_config_finalize(sg_config* cfg) {
         cfg->step_size = 0.07;
         cfg->max_abs_vel_angle = 6.0;
         const int P = cfg->n_planets;
-        if (P < 2 || P > SG_MAX_PLANETS) return SG_ERR_INVALID;  // n_planets = 1 is broken upstream
+        if (P < 1 || P > SG_MAX_PLANETS) return SG_ERR_INVALID;
+        if (P == 1) {
+            // goal.py:79-82 (_init_one_planet): no tiling.  Upstream this configuration cannot take a step
+            // (SURVEY §2.2-10); the semantics offered are the reference's with goal.py:134 and :153 repaired
+            // (tests/golden/make_golden.py: make_goal_one_planet).
+            cfg->rows = cfg->cols = 0;
+            cfg->hex_a = cfg->hex_height = cfg->hex_width = cfg->tiling_width = 0;
+            cfg->planets_radius = 0.8;
+            cfg->goal_radius = 0.2;
+            cfg->ship_radius = 0.2;
+            return SG_OK;
+        }
         const int n_objects = P + 2;
         const int min_tiles = (P == 2) ? n_objects : (int)ceil(n_objects / 0.6);  // hexagonal_tiling.py:26-29
         int r, c;
@@ -2126,8 +2143,11 @@ extern "C" int sg_get_layout(const sg_env* h, sg_layout* out) {
 extern "C" void* sg_state_ptr(const sg_env* h) { return h ? h->state : nullptr; }
 extern "C" uint64_t sg_step_count(const sg_env* h) { return h ? h->step_count : 0; }
 static int sync_step_counters(sg_env* h, cudaStream_t stream) {
-    for (int s = 0; s < h->n_sub; ++s) set_step_counter_kernel<<<1, 1, 0, stream>>>(h->sub[s].dev.q_counts, h->step_count);
-    h->launches += h->n_sub;
+    // one launch for all sub-batches: thread s writes the counter of sub-batch s
+    StepCounterPtrs p{};
+    for (int s = 0; s < h->n_sub; ++s) p.q[s] = h->sub[s].dev.q_counts;
+    set_step_counter_kernel<<<1, 8, 0, stream>>>(p, h->n_sub, h->step_count);
+    h->launches += 1;
     return SG_OK;
 }
 
@@ -2269,7 +2289,8 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
             fused_kernel<TR, OT><<<fused_blocks, kBlock, 0, a.stream>>>(dv, act, obs, rew, dn, tr, (uint32_t)hot_blocks);
         } else if (h->use_staged) {
             int pblocks = hot_blocks < sms * SG_HOT_MINB ? hot_blocks : sms * SG_HOT_MINB;
-            static bool attr_set = false;  // per instantiation
+            static bool attr_set_dev[64] = {};  // function attributes are per device (and per instantiation)
+            bool& attr_set = attr_set_dev[h->device & 63];
             if (!attr_set) {
                 cudaFuncSetAttribute(hot_staged_kernel<TR, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(HotPipeSmem<TR, OT>));
@@ -2359,7 +2380,8 @@ void launch_np(const sg_env* h, const LaunchArgs& a) {
 }
 
 #if defined(SG_PART)
-#if SG_PART == 0  // the other families are instantiated by parts 1-4
+#if SG_PART == 0  // the other families are instantiated by parts 1-5
+extern template void launch_np<TASK_GOAL, 1>(const sg_env*, const LaunchArgs&);
 extern template void launch_np<TASK_GOAL, 3>(const sg_env*, const LaunchArgs&);
 extern template void launch_np<TASK_GOAL, 4>(const sg_env*, const LaunchArgs&);
 extern template void launch_np<TASK_KEPLER, 1>(const sg_env*, const LaunchArgs&);
@@ -2372,6 +2394,8 @@ template void launch_np<TASK_GOAL, 4>(const sg_env*, const LaunchArgs&);
 template void launch_np<TASK_KEPLER, 1>(const sg_env*, const LaunchArgs&);
 #elif SG_PART == 4
 template void launch_np<TASK_DNC, 1>(const sg_env*, const LaunchArgs&);
+#elif SG_PART == 5
+template void launch_np<TASK_GOAL, 1>(const sg_env*, const LaunchArgs&);
 #endif
 #endif
 
@@ -2388,6 +2412,7 @@ static int enqueue(sg_env* h, const LaunchArgs& a) {
 #else
     if (h->cfg.task == SG_TASK_KEPLER) launch_np<TASK_KEPLER, 1>(h, a);
     else if (h->cfg.task == SG_TASK_DONOTCRASH) launch_np<TASK_DNC, 1>(h, a);
+    else if (h->cfg.n_planets == 1) launch_np<TASK_GOAL, 1>(h, a);
     else if (h->cfg.n_planets == 2) launch_np<TASK_GOAL, 2>(h, a);
     else if (h->cfg.n_planets == 3) launch_np<TASK_GOAL, 3>(h, a);
     else if (h->cfg.n_planets == 4) launch_np<TASK_GOAL, 4>(h, a);
@@ -2461,9 +2486,14 @@ static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a, 
         const int64_t launches_before = h->launches;
         SG_CUDA(h, cudaStreamBeginCapture(origin, cudaStreamCaptureModeRelaxed));
         int rc = enqueue_split_step(h, origin, a);
+        const cudaError_t lerr = cudaGetLastError();  // a launch that failed inside the capture invalidates it
         cudaError_t cerr = cudaStreamEndCapture(origin, &graph);
         h->launches = launches_before;
         if (rc != SG_OK) return rc;
+        if (lerr != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return fail(h, SG_ERR_CUDA, std::string("kernel launch during graph capture: ") + cudaGetErrorString(lerr));
+        }
         if (cerr != cudaSuccess) return fail(h, SG_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(cerr));
         int slot = h->n_graphs;
         if (slot == 16) {  // evict the least recently used entry

@@ -231,7 +231,9 @@ __device__ __forceinline__ void find_new_goal_t(const DevCfg& c, Tiles& t, Draws
 template <class TR>
 __device__ __forceinline__ void reset_env_t(const DevCfg& c, Draws& rng, double (&out)[8 + 2 * TR::NP], Tiles& t,
                                             uint32_t& status) {
-    if (TR::TASK == TASK_GOAL) {
+    if (TR::TASK == TASK_GOAL && !TR::TILED) {
+        reset_goal_one_planet(c, rng, out, status);
+    } else if (TR::TASK == TASK_GOAL) {
         constexpr int P = TR::NP, COLS = TR::NP, n_tiles = TR::NP * TR::NP;
         t.fw0 = t.fw1 = t.fw2 = t.fw3 = 0;
         t.goal_tile = 63u;

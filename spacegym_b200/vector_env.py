@@ -352,6 +352,8 @@ class BatchedSpaceEnv:
                 check(self._L.sg_set_step_count(self._h, int(val)), self._h)
                 continue
             dst = views[k]
+            if dst.numel() == 0:  # a field this configuration does not have (e.g. column shifts without a tiling)
+                continue
             src = torch.as_tensor(val, device=self.device).to(dst.dtype)
             src = src.reshape(self.num_envs, -1).t()
             dst.copy_(src)

@@ -65,6 +65,9 @@ CASES = {
     "donotcrash": ("<DoNotCrashContinuous>", {"ship_steering": 0}),
     "donotcrash_vel": ("<DoNotCrashContinuous>", {"ship_steering": 1}),
     "donotcrash_discrete": ("<DoNotCrashDiscrete>", {"ship_steering": 0}),
+    # GoalEnv with n_planets=1 cannot run upstream (goal.py:134 puts the planet on the sampled goal position, goal.py:153
+    # dereferences the missing tiling); the fixtures patch exactly those two lines (make_goal_one_planet)
+    "goal1p": ("<GoalOnePlanet>", {}),
 }
 
 
@@ -81,6 +84,35 @@ def make_donotcrash(discrete, ship_steering):
         dnc.ShipParams = saved
 
 
+def make_goal_one_planet():
+    """GoalContinuousEnv(n_planets=1) with the registry kwargs of GoalContinuous2P-v0 (gym_space/__init__.py:26-40) and the
+    two statements that keep the one-planet configuration from running replaced; everything else is the reference's."""
+    from gym_space.envs.goal import GoalContinuousEnv
+
+    class GoalOnePlanet(GoalContinuousEnv):
+        def _reset(self):  # goal.py:133-145; :134 `ship_pos, *planets_pos = ...` takes (ship, goal, planet) as (ship, *planets)
+            ship_pos, _unused_goal_pos, planet_pos = self._sample_positions()
+            self.planets[0].center_pos = planet_pos
+            self._resample_goal()
+            ship_angle = self._np_random.uniform(0, 2 * np.pi)
+            velocities_xy = self._np_random.standard_normal(2) * 0.07
+            max_abs_ang_vel = 0.7 * self.max_abs_vel_angle
+            angular_velocity = self._np_random.standard_normal() * max_abs_ang_vel / 3
+            angular_velocity = np.clip(angular_velocity, -max_abs_ang_vel, max_abs_ang_vel)
+            self._ship_state.set(ship_pos, ship_angle, velocities_xy, angular_velocity)
+
+        def _reward(self):  # goal.py:147-158; :153 reads self._hexagonal_tiling._debug (None here): threshold = goal_radius
+            reward = (self.survival_reward_scale + self.goal_vel_reward_scale * self._goal_vel_reward2()
+                      + self.safety_reward_scale * self._safety_reward_simple2())
+            if np.linalg.norm(self.goal_pos - self._ship_state.pos_xy) < self.goal_radius:
+                reward += self.goal_sparse_reward
+                self._resample_goal()
+            return reward
+
+    return GoalOnePlanet(n_planets=1, ship_steering=1, ship_moi=0.01, survival_reward_scale=0.2, goal_vel_reward_scale=5.0,
+                         safety_reward_scale=10.0, goal_sparse_reward=5.0, max_engine_force=0.4)
+
+
 def make_env(case):
     env_id, kw = CASES[case]
     with contextlib.redirect_stdout(io.StringIO()):
@@ -90,6 +122,8 @@ def make_env(case):
             env = KeplerDiscreteEnv(**kw)
         elif env_id.startswith("<DoNotCrash"):
             env = make_donotcrash(env_id == "<DoNotCrashDiscrete>", **kw)
+        elif env_id == "<GoalOnePlanet>":
+            env = make_goal_one_planet()
         else:
             env = gym.make(env_id, **kw).unwrapped
     return env
@@ -237,7 +271,8 @@ def harvest_resets(case, n, seed):
         env._np_random = tape
         saved = np.random.uniform
         if goal:
-            env._hexagonal_tiling._np_random = tape
+            if env._hexagonal_tiling is not None:
+                env._hexagonal_tiling._np_random = tape
         else:
             np.random.uniform = lambda: tape._u()  # kepler.py:258-259 (global RNG)
         try:
@@ -251,7 +286,18 @@ def harvest_resets(case, n, seed):
         out["goal"].append(env.goal_pos.copy() if goal else np.zeros(2))
         out["orbit"].append(orbit_of(env))
         out["u_used"].append(tape.iu)
-        if goal:
+        if goal and env._hexagonal_tiling is None:  # one planet: no tile state; successive goals around the planet
+            out["tiles"].append(np.zeros(5 + 64, dtype=np.int64))
+            gs, us = [], []
+            for _g in range(N_GOALS):
+                env._resample_goal()
+                gs.append(env.goal_pos.copy())
+                us.append(tape.iu)
+            out["goals_seq"].append(gs)
+            out["tiles_seq"].append(np.zeros((N_GOALS, 3), dtype=np.int64))
+            out["free_seq"].append(np.zeros((N_GOALS, 64), dtype=np.int64))
+            out["u_used_seq"].append(us)
+        elif goal:
             ht = env._hexagonal_tiling
             free = list(ht._free_tiles_nrs) + [-1] * (64 - len(ht._free_tiles_nrs))
             out["tiles"].append(np.array([int(ht._case_b), int(ht._flip_xy), ht._ship_tile_nr, ht._goal_tile_nr,
@@ -288,7 +334,8 @@ def harvest_reset_samples(case, n, seed):
         pl.append(np.array([p.center_pos for p in env.planets]))
         gl.append(env.goal_pos.copy() if goal else np.zeros(2))
         orb.append(orbit_of(env))
-        same.append(int(goal and env._hexagonal_tiling._goal_tile_nr == env._hexagonal_tiling._ship_tile_nr))
+        ht = env._hexagonal_tiling if goal else None
+        same.append(int(ht is not None and ht._goal_tile_nr == ht._ship_tile_nr))
     return dict(state=np.array(st, dtype=np.float32), planets=np.array(pl, dtype=np.float32),
                 goal=np.array(gl, dtype=np.float32), orbit=np.array(orb, dtype=np.float32),
                 same_tile=np.array(same, dtype=np.int8))
@@ -305,7 +352,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"transitions_{case}.npz"), **tr)
         print(case, "transitions", len(tr["reward"]), "done", int(tr["done"].sum()), "goal",
               int(tr["goal_reached"].sum()), "multi", int((tr["n_steps"] >= 2).sum()), flush=True)
-    for ci, case in enumerate(("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random", "donotcrash")):
+    for ci, case in enumerate(("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random", "donotcrash", "goal1p")):
         if only and case not in only:
             continue
         rs = harvest_resets(case, 64, seed=5000 + ci)

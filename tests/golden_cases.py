@@ -23,9 +23,11 @@ CASES = {
     "donotcrash": ("DoNotCrashContinuous-v0", {}),
     "donotcrash_vel": ("DoNotCrashContinuous-v0", {"ship_steering": 1}),
     "donotcrash_discrete": ("DoNotCrashDiscrete-v0", {}),
+    # GoalEnv with one planet: goal.py:134,153 patched (make_golden.py: make_goal_one_planet)
+    "goal1p": ("GoalContinuous2P-v0", {"n_planets": 1}),
 }
 
-RESET_CASES = ("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random", "donotcrash")
+RESET_CASES = ("goal2p", "goal3p", "goal4p", "kepler_circle", "kepler_random", "donotcrash", "goal1p")
 
 # the parity bar: |delta| <= TOL * max(1, |ref|)  (BASELINE.json north_star: 1e-9 in FP64)
 TOL = 1e-9

@@ -68,8 +68,13 @@ def test_registry_error_behaviour():
         sg.make_config("NoSuchEnv-v0")
     with pytest.raises(TypeError):
         sg.make_config("GoalContinuous3P-v0", ref_orbit_a=1.0)  # a Kepler kwarg on a Goal env
+    one = sg.make_config("GoalContinuous3P-v0", n_planets=1)  # goal.py:79-82: no tiling, radii 0.8 / 0.2 / 0.2
+    assert (one.n_planets, one.rows, one.cols, one.planets_radius, one.goal_radius, one.ship_radius) == (1, 0, 0, 0.8, 0.2, 0.2)
+    assert lib().sg_obs_dim(C.byref(one)) == 11
     with pytest.raises(ValueError):
-        sg.make_config("GoalContinuous3P-v0", n_planets=1)  # broken upstream too
+        sg.make_config("GoalContinuous3P-v0", n_planets=0)
+    with pytest.raises(ValueError):
+        sg.make_config("GoalContinuous3P-v0", n_planets=5)
     with pytest.raises(ValueError):
         sg.make_config("GoalContinuous3P-v0", ship_steering=2)
 
