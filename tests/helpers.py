@@ -43,8 +43,9 @@ def oracle_state_to_engine(cfg, envs):
         P = cfg.n_planets
         st["planets"] = envs["planets"][:, :2 * P].copy()
         st["goal"] = envs["goal"].copy()
-        st["col_shift"] = envs["col_shift"][:, :cfg.cols].copy()
-        st["tile_word"], st["free_tiles"] = pack_tiles(envs)
+        if cfg.cols > 0:  # the one-planet GoalEnv has no tiling (goal.py:79-82)
+            st["col_shift"] = envs["col_shift"][:, :cfg.cols].copy()
+            st["tile_word"], st["free_tiles"] = pack_tiles(envs)
     elif cfg.task == 1:
         st["orbit"] = np.stack([envs["orbit_ecc"], envs["orbit_angle"]], axis=1)
     return st
@@ -61,10 +62,11 @@ def compare_engine_to_oracle(cfg, dev_state, envs, tol=TOL):
         n = len(envs)
         ok &= close(dev_state["planets"].cpu().numpy().reshape(n, 2 * P), envs["planets"][:, :2 * P], tol).all(axis=1)
         ok &= close(dev_state["goal"].cpu().numpy(), envs["goal"], tol).all(axis=1)
-        ok &= close(dev_state["col_shift"].cpu().numpy().reshape(n, -1), envs["col_shift"][:, :cfg.cols], tol).all(axis=1)
-        word, fw = pack_tiles(envs)
-        ok &= dev_state["tile_word"].cpu().numpy() == word
-        ok &= (dev_state["free_tiles"].cpu().numpy().reshape(n, 4) == fw).all(axis=1)
+        if cfg.cols > 0:  # tile state exists only with a hexagonal tiling (n_planets >= 2)
+            ok &= close(dev_state["col_shift"].cpu().numpy().reshape(n, -1), envs["col_shift"][:, :cfg.cols], tol).all(axis=1)
+            word, fw = pack_tiles(envs)
+            ok &= dev_state["tile_word"].cpu().numpy() == word
+            ok &= (dev_state["free_tiles"].cpu().numpy().reshape(n, 4) == fw).all(axis=1)
     elif cfg.task == 1:
         ok &= close(dev_state["orbit"].cpu().numpy(),
                     np.stack([envs["orbit_ecc"], envs["orbit_angle"]], axis=1), tol).all(axis=1)
