@@ -32,7 +32,7 @@ COLS = [
     "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
     "smsp__warps_eligible.avg.per_cycle_active",
 ]
-KERNELS = ("hot_kernel", "cont_kernel", "tail_kernel")
+KERNELS = ("hot_kernel", "cont_kernel", "tail2_kernel")  # round 1: tail_kernel
 
 
 def main():
@@ -49,6 +49,11 @@ def main():
         scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}
         traffic[k] = int(sum(float(d[m]) * scale[u[m].lower()] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
         shutil.copy(src(f"{k}_summary.txt"), dst(f"{k}_stalls.txt"))
+        if os.path.exists(src(f"{k}_source.csv.gz")):  # dynamic instruction mix (tools/ncu_dynamic_mix.py)
+            import subprocess
+            mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_dynamic_mix.py"), src(f"{k}_source.csv.gz")],
+                                 capture_output=True, text=True).stdout
+            open(dst(f"{k}_dynamic_mix.txt"), "w").write(mix)
         print(k, d["gpu__time_duration.sum"], "us", d["launch__registers_per_thread"], "regs, issue",
               d["smsp__issue_active.avg.pct_of_peak_sustained_active"], "fp64",
               d["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"], "inst", d["smsp__inst_executed.sum"])
@@ -79,7 +84,7 @@ def main():
           {k: round(v / tot, 3) for k, v in mean.items()})
     b = json.load(open(dst("bench_final.json")))
     kt = b["kernel_times"]
-    ev = {"hot_kernel": kt["hot_us"], "cont_kernel": kt["cont_us"], "tail_kernel": kt["tail_us"]}
+    ev = {"hot_kernel": kt["hot_us"], "cont_kernel": kt["cont_us"], KERNELS[2]: kt["tail_us"]}
     print("CUDA events (us):", {k: round(v, 1) for k, v in ev.items()}, "shares:",
           {k: round(v / sum(ev.values()), 3) for k, v in ev.items()})
     print("value", b["value"], "e2e", b["e2e"]["value"], "roofline", b["roofline"]["frac"], b["roofline_fp64"]["frac"],
