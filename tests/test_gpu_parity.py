@@ -440,6 +440,25 @@ def test_config5_goal4p_4m_envs_sharded(oracle):
         e.close()
 
 
+def test_config5_goal4p_8m_envs_one_handle(oracle):
+    """Top of BASELINE configs[4] on one GPU: ONE GoalContinuous4P-v0 handle of 8M envs (it splits
+    itself into sub-batches): allocation, reset, 10 steps, integrity of every env, oracle spot check of one more step."""
+    n = 1 << 23
+    cfg = oracle.config_from_id("GoalContinuous4P-v0")
+    env = sg.make("GoalContinuous4P-v0", n, seed=9, copy=False)
+    obs = env.reset()
+    assert obs.shape == (n, 17) and bool(torch.isfinite(obs).all())
+    env.rollout_random(10)
+    assert _spot_check_against_oracle(oracle, "goal", env, cfg, 500, np.random.RandomState(3)) == 0
+    v = env.state_views()  # field-major views of the state block: no env-major copies of 8M rows
+    assert int((v["status"] != 0).sum()) == 0, "sticky fault bits"
+    assert bool(torch.isfinite(v["ship"]).all()) and bool((v["ship"][:2].abs() <= 1.5).all())
+    assert int(v["elapsed"].max()) <= 11
+    st = env.stats()
+    assert st["episodes"] > 0.005 * 11 * n
+    env.close()
+
+
 @pytest.mark.parametrize("env_id", ["GoalContinuous3P-v0", "DoNotCrashContinuous-v0"])
 def test_trajectory_dump_and_headless_replay(env_id, tmp_path):
     """recorded state -> .npz -> software-rendered frames (gym_space/rendering.py geometry)."""
