@@ -62,6 +62,62 @@ __device__ __forceinline__ double fast_div(double a, double b) {
     return fma(fma(-b, q, a), y, q);  // residual correction
 }
 
+// min / max by one compare and a select.  CUDA's fmin / fmax implement the IEEE NaN rules and cost ~9 instructions on
+// doubles here (DSETP with two predicates, quiet-bit LOP3, five moves / selects); the hot path calls them ~20 times per
+// env step.  sel_min(a, b) / sel_max(a, b) return a unless b is strictly smaller / larger — Python's min / max, which
+// is what SciPy's step-size rules use — so a NaN in b falls back to a: call sites pass the bound that must survive
+// as a.  For ordered operands the results equal fmin / fmax.
+#ifndef SG_FAST_MINMAX
+#define SG_FAST_MINMAX 1
+#endif
+#if SG_FAST_MINMAX
+__device__ __forceinline__ double sel_min(double a, double b) { return b < a ? b : a; }
+__device__ __forceinline__ double sel_max(double a, double b) { return b > a ? b : a; }
+#else
+__device__ __forceinline__ double sel_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double sel_max(double a, double b) { return fmax(a, b); }
+#endif
+
+// ---- sin / cos for a in [0, 2 pi] (wrapped headings, reset angles, Box-Muller angles) ------------------------
+// a = q pi/2 + r with q = rint(a 2/pi) in 0..4, |r| <= pi/4 (two-constant Cody-Waite: q is tiny, so q * hi is
+// exact); sin r through r^15, cos r through r^16: truncation errors < 5e-17 / 2e-18 at |r| = pi/4.
+__device__ __forceinline__ void sincos_2pi(double a, double& sn, double& cs) {
+    const double q = rint(a * 0.63661977236758134308);  // 2 / pi
+    double r = fma(-q, 1.5707963267948965580, a);        // pi/2 (hi)
+    r = fma(-q, 6.1232339957367660359e-17, r);           // pi/2 (lo)
+    const double r2 = r * r;
+    double ps = fma(r2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+    double pc = fma(r2, 1.0 / 20922789888000.0, -1.0 / 87178291200.0);
+    ps = fma(ps, r2, -1.0 / 39916800.0);
+    pc = fma(pc, r2, 1.0 / 479001600.0);
+    ps = fma(ps, r2, 1.0 / 362880.0);
+    pc = fma(pc, r2, -1.0 / 3628800.0);
+    ps = fma(ps, r2, -1.0 / 5040.0);
+    pc = fma(pc, r2, 1.0 / 40320.0);
+    ps = fma(ps, r2, 1.0 / 120.0);
+    pc = fma(pc, r2, -1.0 / 720.0);
+    ps = fma(ps, r2, -1.0 / 6.0);
+    pc = fma(pc, r2, 1.0 / 24.0);
+    const double s = fma(ps * r2, r, r);
+    pc = fma(pc, r2, -0.5);
+    const double c = fma(pc, r2, 1.0);
+    const int k = (int)q & 3;
+    const double s1 = (k & 1) ? c : s, c1 = (k & 1) ? s : c;
+    sn = (k & 2) ? -s1 : s1;
+    cs = ((k + 1) & 2) ? -c1 : c1;
+}
+
+
+// out-of-line sincos for the cold paths (reset placement, terminal states): one copy of the range reduction
+static __device__ __noinline__ void sincos_cold(double a, double* s, double* c) { sincos(a, s, c); }
+// SG_FAST_SINCOS0 (option, off): quadrant-reduction sincos for the wrapped heading at the start of a step, library
+// routine behind a call for headings injected from outside [0, 2 pi].  74 -> ~35 executed instructions, but the hot
+// kernel went from 36.4 to 38.6 us (5.89e9 vs 6.05e9 env-steps/s): the call in the kernel body costs more than the
+// shorter sequence returns.  Select-based min / max alone: 6.08e9 vs 6.05e9, adopted.
+#ifndef SG_FAST_SINCOS0
+#define SG_FAST_SINCOS0 0
+#endif
+
 // ---- x^(1/5) and x^(-1/10) without pow ----------------------------------------------------------------
 // The step-size rules need (0.01 / d)^(1/5) (scipy:common.py:131) and err^(-1/5) = (err^2)^(-1/10)
 // (scipy:rk.py:150-161).  CUDA's pow is a ~200-instruction serial chain behind a CALL that a warp walks
@@ -100,7 +156,7 @@ __device__ __forceinline__ double inv_tenth_root(double x) { return pow(x, -0.1)
 // shrinks by max(0.2, .) = 0.2 as it does in SciPy (where the comparison with NaN fails), and the attempt loop
 // ends at min_step with "step size too small" instead of never ending.
 __device__ __forceinline__ double controller_factor(double err2) {
-    const double e = (err2 <= 1e10) ? fmax(err2, 1e-14) : 1e10;
+    const double e = (err2 <= 1e10) ? sel_max(1e-14, err2) : 1e10;
     return 0.9 * inv_tenth_root(e);
 }
 
@@ -523,8 +579,8 @@ __device__ __forceinline__ void event_values_from_pd(const DevCfg& c, double x, 
         g[0] = pd[0] - c.r0;
         g[1] = pd[0] - c.r1;
     }
-    g[TR::NEV - 3] = fmin(c.half_ws - x, c.half_ws - y);
-    g[TR::NEV - 2] = fmin(c.half_ws + x, c.half_ws + y);
+    g[TR::NEV - 3] = sel_min(c.half_ws - x, c.half_ws - y);
+    g[TR::NEV - 2] = sel_min(c.half_ws + x, c.half_ws + y);
     g[TR::NEV - 1] = c.om_max - fabs(om);
 }
 
@@ -754,7 +810,14 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     if (TR::STEER == STEER_VEL) e.om = act.w;  // the RHS overwrites omega in place
     S.x = e.x; S.y = e.y; S.th = e.th; S.vx = e.vx; S.vy = e.vy; S.om = e.om;
     S.t = 0.0;
+#if SG_FAST_SINCOS0
+    // the heading of a stepped env is wrapped to [0, 2 pi) (wrap_ship_angle): quadrant reduction + Taylor, no slow
+    // path; states injected from outside the range take the library routine
+    if (S.th >= 0.0 && S.th <= kTwoPi) sincos_2pi(S.th, S.sth, S.cth);
+    else sincos_cold(S.th, &S.sth, &S.cth);
+#else
     sincos(S.th, &S.sth, &S.cth);
+#endif
     double ipd0[TR::NP];
     accel_pd<TR>(c, e, S.x, S.y, S.cth, S.sth, S.fs, S.Ax, S.Ay, pd, ipd0);  // f0 (+ planet distances for g(t0))
     const double x = S.x, y = S.y, th = S.th, vx = S.vx, vy = S.vy, om = S.om, alpha = S.alpha;
@@ -778,7 +841,7 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     // comparison of scipy:common.py:118-132 is monotone in the norm, h0 = 0.01 d0 / d1 = 0.01 sqrt(S0 / S1) needs
     // one reciprocal and one square root instead of two square roots and a division, and d2 is never divided out.
     double h0 = (S0 < 6e-10 || S1 < 6e-10) ? 1e-6 : 0.01 * fast_sqrt(S0 * fast_rcp(S1));
-    h0 = fmin(h0, T);
+    h0 = sel_min(T, h0);
     double Bx, By, cn, sn;
     const double dprobe = h0 * om;
     accel_rot(c, e, S, x + h0 * vx, y + h0 * vy, dprobe, fabs(dprobe) < 0.5, Bx, By, cn, sn);  // f(y0 + h0 f0)
@@ -788,25 +851,23 @@ __device__ __forceinline__ void init_step(const DevCfg& c, EnvRegs<TR>& e, const
     q = (Bx - S.Ax) * rvx; S2 = fma(q, q, S2);
     q = (By - S.Ay) * rvy; S2 = fma(q, q, S2);
     const double hq = 6.0 * (h0 * h0);
-    const double M = fmax(S1 * (h0 * h0), S2);  // = 6 h0^2 max(d1, d2)^2
-    const double lim = fmin(100 * h0, T);
+    const double M = sel_max(S1 * (h0 * h0), S2);  // = 6 h0^2 max(d1, d2)^2
+    const double lim = sel_min(T, 100 * h0);
     double h_abs;
     if (S1 <= 6e-30 && S2 <= 1e-30 * hq) {  // d1 <= 1e-15 and d2 <= 1e-15
-        h_abs = fmin(lim, fmax(1e-6, h0 * 1e-3));
+        h_abs = sel_min(lim, sel_max(1e-6, h0 * 1e-3));
     } else {
         // h1 = (0.01 / dm) ** 0.2 only matters when it is below lim: decide that without the root
         // (0.01 >= dm lim^5  <=>  1e-4 * 6 h0^2 >= M lim^10), and pay for it only on the lanes that need its value:
         // h1 = (dm^2 / 1e-4) ** (-1/10).
         const double l2 = lim * lim, l5 = l2 * l2 * lim;
         if (1e-4 * hq >= M * (l5 * l5) * 1.0000000002) h_abs = lim;
-        else h_abs = fmin(lim, inv_tenth_root(fmin(fmax(fast_div(1e4 * M, hq), 1e-30), 1e30)));
+        else h_abs = sel_min(lim, inv_tenth_root(sel_min(1e30, sel_max(1e-30, fast_div(1e4 * M, hq)))));
     }
     S.h_abs = h_abs;
     event_values_from_pd<TR>(c, x, y, om, pd, g);
 }
 
-// out-of-line sincos for the cold paths (reset placement, terminal states): one copy of the range reduction
-static __device__ __noinline__ void sincos_cold(double a, double* s, double* c) { sincos(a, s, c); }
 
 struct SinCos6 {
     double s[6], c[6];
@@ -967,10 +1028,10 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     double ey = hh * (HT(eb1) * Ay[0] + HT(eb2) * Ay[1] + HT(eb3) * Ay[2] + HT(eb4) * Ay[3] + HT(eb5) * Ay[4] + HT(eb6) * Ay[5]);
     double evx = h * (HT(e1) * Ax[0] + HT(e3) * Ax[2] + HT(e4) * Ax[3] + HT(e5) * Ax[4] + HT(e6) * Ax[5] + HT(e7) * Ax[6]);
     double evy = h * (HT(e1) * Ay[0] + HT(e3) * Ay[2] + HT(e4) * Ay[3] + HT(e5) * Ay[4] + HT(e6) * Ay[5] + HT(e7) * Ay[6]);
-    ex *= fast_rcp(HT(atol) + fmax(fabs(x), fabs(xn)) * HT(rtol));
-    ey *= fast_rcp(HT(atol) + fmax(fabs(y), fabs(yn)) * HT(rtol));
-    evx *= fast_rcp(HT(atol) + fmax(fabs(vx), fabs(vxn)) * HT(rtol));
-    evy *= fast_rcp(HT(atol) + fmax(fabs(vy), fabs(vyn)) * HT(rtol));
+    ex *= fast_rcp(HT(atol) + sel_max(fabs(x), fabs(xn)) * HT(rtol));
+    ey *= fast_rcp(HT(atol) + sel_max(fabs(y), fabs(yn)) * HT(rtol));
+    evx *= fast_rcp(HT(atol) + sel_max(fabs(vx), fabs(vxn)) * HT(rtol));
+    evy *= fast_rcp(HT(atol) + sel_max(fabs(vy), fabs(vyn)) * HT(rtol));
     err2 = (ex * ex + ey * ey + evx * evx + evy * evy) * HT(sixth);  // error_norm ** 2
 }
 
@@ -1075,10 +1136,10 @@ __device__ __forceinline__ void rk_attempt_sm(const DevCfg& c, const EnvRegs<TR>
     accel_pd<TR>(c, e, xn, yn, cn, sn, S.fs, A6x, A6y, pdn, ipdn);
     double evx = h * (pvx + HT(e7) * A6x);
     double evy = h * (pvy + HT(e7) * A6y);
-    ex *= fast_rcp(HT(atol) + fmax(fabs(x), fabs(xn)) * HT(rtol));
-    ey *= fast_rcp(HT(atol) + fmax(fabs(y), fabs(yn)) * HT(rtol));
-    evx *= fast_rcp(HT(atol) + fmax(fabs(vx), fabs(vxn)) * HT(rtol));
-    evy *= fast_rcp(HT(atol) + fmax(fabs(vy), fabs(vyn)) * HT(rtol));
+    ex *= fast_rcp(HT(atol) + sel_max(fabs(x), fabs(xn)) * HT(rtol));
+    ey *= fast_rcp(HT(atol) + sel_max(fabs(y), fabs(yn)) * HT(rtol));
+    evx *= fast_rcp(HT(atol) + sel_max(fabs(vx), fabs(vxn)) * HT(rtol));
+    evy *= fast_rcp(HT(atol) + sel_max(fabs(vy), fabs(vyn)) * HT(rtol));
     err2 = (ex * ex + ey * ey + evx * evx + evy * evy) * HT(sixth);
 }
 
@@ -1092,13 +1153,13 @@ __device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t,
 __device__ __forceinline__ bool controller(double err2, bool& rejected, bool more_steps, double& h_abs) {
     if (err2 < 1) {
         if (more_steps) {  // the next step size only matters if another step follows
-            double factor = (err2 == 0) ? 10.0 : fmin(10.0, controller_factor(err2));
-            if (rejected) factor = fmin(1.0, factor);
+            double factor = (err2 == 0) ? 10.0 : sel_min(10.0, controller_factor(err2));
+            if (rejected) factor = sel_min(1.0, factor);
             h_abs *= factor;
         }
         return true;
     }
-    h_abs *= fmax(0.2, controller_factor(err2));
+    h_abs *= sel_max(0.2, controller_factor(err2));
     rejected = true;
     return false;
 }

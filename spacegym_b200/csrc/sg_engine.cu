@@ -968,8 +968,13 @@ __device__ __forceinline__ void prefetch_chunk_l2(const DevCfg& c, const float* 
     else if (threadIdx.x < 12 && actions) prefetch_l2(actions + 2 * first + 32 * (threadIdx.x - 4));
 }
 
+#ifdef SG_HOT_MAXREG  // experiment: register cap independent of the CTA count ptxas derives it from
+#define SG_HOT_BOUNDS __maxnreg__(SG_HOT_MAXREG)
+#else
+#define SG_HOT_BOUNDS __launch_bounds__(kBlock, SG_HOT_MINB)
+#endif
 template <class TR, typename OT>
-__global__ void __launch_bounds__(kBlock, SG_HOT_MINB)
+__global__ void SG_HOT_BOUNDS
 hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
 #if SG_HOT_SMEM_A

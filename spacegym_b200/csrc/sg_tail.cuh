@@ -19,34 +19,7 @@
 
 namespace sg {
 
-// ---- sin / cos for a in [0, 2 pi] (reset angles, Box-Muller angles) --------------------------------------------
-// a = q pi/2 + r with q = rint(a 2/pi) in 0..4, |r| <= pi/4 (two-constant Cody-Waite: q is tiny, so q * hi is
-// exact); sin r through r^15, cos r through r^16: truncation errors < 5e-17 / 2e-18 at |r| = pi/4.
-__device__ __forceinline__ void sincos_2pi(double a, double& sn, double& cs) {
-    const double q = rint(a * 0.63661977236758134308);  // 2 / pi
-    double r = fma(-q, 1.5707963267948965580, a);        // pi/2 (hi)
-    r = fma(-q, 6.1232339957367660359e-17, r);           // pi/2 (lo)
-    const double r2 = r * r;
-    double ps = fma(r2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
-    double pc = fma(r2, 1.0 / 20922789888000.0, -1.0 / 87178291200.0);
-    ps = fma(ps, r2, -1.0 / 39916800.0);
-    pc = fma(pc, r2, 1.0 / 479001600.0);
-    ps = fma(ps, r2, 1.0 / 362880.0);
-    pc = fma(pc, r2, -1.0 / 3628800.0);
-    ps = fma(ps, r2, -1.0 / 5040.0);
-    pc = fma(pc, r2, 1.0 / 40320.0);
-    ps = fma(ps, r2, 1.0 / 120.0);
-    pc = fma(pc, r2, -1.0 / 720.0);
-    ps = fma(ps, r2, -1.0 / 6.0);
-    pc = fma(pc, r2, 1.0 / 24.0);
-    const double s = fma(ps * r2, r, r);
-    pc = fma(pc, r2, -0.5);
-    const double c = fma(pc, r2, 1.0);
-    const int k = (int)q & 3;
-    const double s1 = (k & 1) ? c : s, c1 = (k & 1) ? s : c;
-    sn = (k & 2) ? -s1 : s1;
-    cs = ((k + 1) & 2) ? -c1 : c1;
-}
+// sincos_2pi (sin / cos for angles in [0, 2 pi]: reset angles, Box-Muller angles) lives in sg_device.cuh.
 
 // ---- draw session on precomputed Philox blocks ------------------------------------------------------------------
 // Same stream as Rng (sg_device.cuh): block b of env stream 0 = Philox(counter (env_lo, env_hi, ctr + b, 0), key seed)
