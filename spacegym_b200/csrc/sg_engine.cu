@@ -42,6 +42,12 @@ namespace sg {
 #define SG_KBLOCK 128
 #endif
 constexpr int kBlock = SG_KBLOCK;  // threads per CTA of every kernel but the tail kernel
+// SG_CONT_GATHER: the hot kernel writes a 16-row continuation record (integrator state + action terms) and the
+// continuation kernel gathers the scene (planets, goal / orbit) and the step's start position from the state block
+// by env index, instead of a 26-row record with everything in coalesced scratch rows.
+#ifndef SG_CONT_GATHER
+#define SG_CONT_GATHER 1
+#endif
 
 // ---- state access ---------------------------------------------------------------------------
 #ifndef SG_LD_MODE
@@ -567,7 +573,10 @@ __device__ __forceinline__ void save_cont(const DevCfg& c, uint32_t* q_idx, doub
     if (write_index) q_idx[slot] = (uint32_t)i;
     p[0 * cap] = S.x; p[1 * cap] = S.y; p[2 * cap] = S.th; p[3 * cap] = S.vx; p[4 * cap] = S.vy; p[5 * cap] = S.om;
     p[6 * cap] = S.cth; p[7 * cap] = S.sth; p[8 * cap] = S.Ax; p[9 * cap] = S.Ay; p[10 * cap] = S.h_abs;
-    p[11 * cap] = S.t; p[12 * cap] = lx; p[13 * cap] = ly; p[14 * cap] = rejected ? 1.0 : 0.0;
+    p[11 * cap] = S.t; p[14 * cap] = rejected ? 1.0 : 0.0;
+    if (!SG_CONT_GATHER) {  // otherwise the continuation kernel re-reads the step's start position from the state block
+        p[12 * cap] = lx; p[13 * cap] = ly;
+    }
 }
 
 // everything else the single-attempt continuation kernel needs, so that it reads coalesced scratch rows
@@ -578,6 +587,7 @@ __device__ __forceinline__ void save_cont_scene(const DevCfg& c, double* scr, ui
     const long long cap = c.q_cap;
     double* p = scr + slot;
     p[15 * cap] = act.fs; p[16 * cap] = act.alpha; p[17 * cap] = act.act_term;
+    if (SG_CONT_GATHER) return;  // planets / goal / orbit: gathered from the state block by env index
     if (TR::TASK == TASK_GOAL) {
 #pragma unroll
         for (int q = 0; q < TR::NP; ++q) {
@@ -593,12 +603,32 @@ __device__ __forceinline__ void save_cont_scene(const DevCfg& c, double* scr, ui
 }
 
 template <class TR>
-__device__ __forceinline__ void load_cont_scene(const DevCfg& c, const double* scr, uint32_t j, EnvRegs<TR>& e, Act& act) {
+__device__ __forceinline__ void load_cont_scene(const DevCfg& c, const double* scr, uint32_t j, long long i, EnvRegs<TR>& e,
+                                                Act& act) {
     const long long cap = c.q_cap;
     const double* p = scr + j;
     act.fs = p[15 * cap]; act.alpha = p[16 * cap]; act.act_term = p[17 * cap];
     act.w = 0.0;
     e.x = e.y = e.th = e.vx = e.vy = e.om = 0.0;
+    if (SG_CONT_GATHER) {  // the hot kernel does not touch the scene fields, and the ship rows only of finished envs
+        const long long n = c.stride;
+        if (TR::TASK == TASK_GOAL) {
+#pragma unroll
+            for (int q = 0; q < TR::NP; ++q) {
+                e.px[q] = c.planets[(2 * q) * n + i];
+                e.py[q] = c.planets[(2 * q + 1) * n + i];
+            }
+            e.gx = c.goal[i];
+            e.gy = c.goal[n + i];
+            e.ecc = e.ang = 0.0;
+        } else {
+            e.px[0] = e.py[0] = 0.0;
+            e.gx = e.gy = 0.0;
+            e.ecc = (TR::TASK == TASK_KEPLER) ? c.orbit[i] : 0.0;
+            e.ang = (TR::TASK == TASK_KEPLER) ? c.orbit[n + i] : 0.0;
+        }
+        return;
+    }
     if (TR::TASK == TASK_GOAL) {
 #pragma unroll
         for (int q = 0; q < TR::NP; ++q) {
@@ -998,14 +1028,18 @@ hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ o
 }
 
 template <class TR>
-__device__ __forceinline__ void load_cont(const DevCfg& c, const double* scr, uint32_t j, const Act& act, Integ<TR>& S,
-                                          double& lx, double& ly, bool& rejected) {
+__device__ __forceinline__ void load_cont(const DevCfg& c, const double* scr, uint32_t j, long long i, const Act& act,
+                                          Integ<TR>& S, double& lx, double& ly, bool& rejected) {
     const long long cap = c.q_cap;
     const double* p = scr + j;
     S.x = p[0 * cap]; S.y = p[1 * cap]; S.th = p[2 * cap]; S.vx = p[3 * cap]; S.vy = p[4 * cap];
     S.om = p[5 * cap]; S.cth = p[6 * cap]; S.sth = p[7 * cap]; S.Ax = p[8 * cap]; S.Ay = p[9 * cap];
     S.h_abs = p[10 * cap]; S.t = p[11 * cap];
-    lx = p[12 * cap]; ly = p[13 * cap];
+    if (SG_CONT_GATHER) {  // env.last_xy = the position the step started from: still in the state block
+        lx = c.ship[i]; ly = c.ship[c.stride + i];
+    } else {
+        lx = p[12 * cap]; ly = p[13 * cap];
+    }
     rejected = p[14 * cap] != 0.0;
     S.alpha = (TR::STEER == STEER_ACC) ? act.alpha : 0.0;
     S.fs = act.fs;
@@ -1065,8 +1099,8 @@ __device__ __forceinline__ void cont1_entry(const DevCfg& c, uint32_t j, bool va
     if (valid) {
         const uint32_t elapsed0 = c.elapsed[i];
         const double ep_ret0 = c.ep_return[i];
-        load_cont_scene<TR>(c, c.scr_cont, j, e, act);
-        load_cont<TR>(c, c.scr_cont, j, act, S, lx, ly, rejected);
+        load_cont_scene<TR>(c, c.scr_cont, j, i, e, act);
+        load_cont<TR>(c, c.scr_cont, j, i, act, S, lx, ly, rejected);
         double g[TR::NEV], pd[TR::NP];
         event_values(c, e, S.x, S.y, S.om, g, pd);
         // one pass of the attempt loop of _step_impl (scipy:rk.py:119-165)
@@ -1240,11 +1274,11 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
             SG_CHK(chk_consume(c, 0, i);)
             EnvRegs<TR> e;
             Act act;
-            load_cont_scene<TR>(c, scr_in, j, e, act);  // planets / goal / action terms: coalesced scratch rows, no gather
+            load_cont_scene<TR>(c, scr_in, j, i, e, act);  // planets / goal / action terms: coalesced scratch rows, no gather
             bool rejected;
             const uint32_t elapsed0 = c.elapsed[i];
             const double ep_ret0 = c.ep_return[i];
-            load_cont<TR>(c, scr_in, j, act, S, lx, ly, rejected);
+            load_cont<TR>(c, scr_in, j, i, act, S, lx, ly, rejected);
             double g[TR::NEV], pd[TR::NP];
             event_values(c, e, S.x, S.y, S.om, g, pd);
             const int rc = rk_loop<TR>(c, e, S, g, rejected, &io, pd);
