@@ -1464,6 +1464,9 @@ constexpr int kTail2Block = 64;
 #ifndef SG_TAIL2_MINB
 #define SG_TAIL2_MINB 4
 #endif
+#ifndef SG_TAIL2_FENCE
+#define SG_TAIL2_FENCE 0
+#endif
 template <class TR, typename OT>
 __global__ void __launch_bounds__(kTail2Block, SG_TAIL2_MINB)
 tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
@@ -1638,9 +1641,13 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
     pdl_trigger();
     warp_stats_flush(c, st);
     // the last block to finish empties the queues for the next step
+    // (no __threadfence(): nothing the last block writes is read again inside this kernel — every block read the
+    // counters and the step number before its sweep, and the next kernel starts behind the kernel boundary)
     __shared__ bool last;
     __syncthreads();
+#if SG_TAIL2_FENCE
     __threadfence();
+#endif
     if (threadIdx.x == 0) last = (atomicAdd(&c.q_counts[3], 1u) == gridDim.x - 1);
     __syncthreads();
     if (last) {  // ... and advances the device-side step counter that keys the synthetic-action stream
@@ -2403,14 +2410,22 @@ struct LaunchArgs {
     cudaStream_t hi_stream;  // OP_STEP_SPLIT: stream of the small kernels (nullptr: same stream)
 };
 
+template <typename... KArgs, typename... Args>
+static void launch_k_smem(void (*kernel)(KArgs...), int grid, int block, int dyn_smem, cudaStream_t stream, bool pdl,
+                          Args... args);
 // Launch with (pdl = true) programmatic stream serialization: the grid may start while the previous kernel of the
 // stream drains; the kernels order themselves with pdl_wait().
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, bool pdl, Args... args) {
+    launch_k_smem(kernel, grid, block, 0, stream, pdl, args...);
+}
+template <typename... KArgs, typename... Args>
+static void launch_k_smem(void (*kernel)(KArgs...), int grid, int block, int dyn_smem, cudaStream_t stream, bool pdl,
+                          Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)dyn_smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -2466,7 +2481,12 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
             hot_staged_kernel<TR, OT><<<pblocks, kBlock, sizeof(HotPipeSmem<TR, OT>), a.stream>>>(dv, act, obs, rew, dn, tr,
                                                                                              (uint32_t)hot_blocks);
         } else {
-            launch_k(hot_kernel<TR, OT>, hot_blocks, kBlock, a.stream, h->use_pdl != 0, dv, act, obs, rew, dn, tr);
+            // SG_HOT_DYNSMEM=<bytes> (measurement aid): unused dynamic shared memory that limits the hot kernel to fewer
+            // CTAs per SM with the SAME binary (38912 -> 3 CTAs, 97280 -> 2), to read its sensitivity to occupancy
+            static const int hot_dyn = getenv("SG_HOT_DYNSMEM") ? atoi(getenv("SG_HOT_DYNSMEM")) : 0;
+            if (hot_dyn > 0)
+                cudaFuncSetAttribute(hot_kernel<TR, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, hot_dyn);
+            launch_k_smem(hot_kernel<TR, OT>, hot_blocks, kBlock, hot_dyn, a.stream, h->use_pdl != 0, dv, act, obs, rew, dn, tr);
         }
         if (h->timing) cudaEventRecord(h->tev[1], a.stream);
         cudaStream_t small = a.stream;

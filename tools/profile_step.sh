@@ -18,6 +18,7 @@ for k in hot_kernel cont_kernel tail2_kernel; do
   python tools/ncu_summary.py gpurun_out/${P}_$k.ncu-rep 30 > gpurun_out/${P}_${k}_summary.txt 2>&1
   ncu -i gpurun_out/${P}_$k.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/${P}_${k}_source.csv.gz
   ls -la gpurun_out/${P}_$k.ncu-rep
-  [ -n "$SG_KEEP_REP" ] || rm -f gpurun_out/${P}_$k.ncu-rep   # gpurun brings back at most 64 MiB
+  # gpurun brings back at most 64 MiB: only the hot kernel's report is kept (tools/ncu_by_line.py reads it)
+  if [ "$k" != "hot_kernel" ] && [ -z "$SG_KEEP_REP" ]; then rm -f gpurun_out/${P}_$k.ncu-rep; fi
   head -12 gpurun_out/${P}_${k}_summary.txt
 done
