@@ -264,8 +264,8 @@ struct DevCfg {
     double* scr_cont2;
     uint32_t* q_event;
     uint32_t* q_post;     // env index | reached << 30 | done << 31
-    double* scr_cont;     // [13][cap]: x y th vx vy om cth sth Ax Ay h_abs t flags(lx, ly separately)
-    double* scr_event;    // [24][cap]
+    double* scr_cont;     // [28][cap] rows, 16 in use: x y th vx vy om cth sth Ax Ay h_abs t (lx ly) rejected | fs alpha act_term | (scene)
+    double* scr_event;    // [25][cap]: x y th vx vy om h t_old Ax[7] Ay[7] lx ly active
     long long q_cap;
     long long n;       // envs of this (sub-)batch
     long long stride;  // field stride of the struct-of-arrays state = envs of the whole handle

@@ -339,7 +339,7 @@ step_kernel(const DevCfg c, const float* __restrict__ actions, int K, unsigned l
 // env (initial step selection + ONE attempt + epilogue) and appends the rest to compact queues, which
 // the continuation and tail kernels process with densely packed warps.
 // =================================================================================================
-constexpr int kContFields = 28;   // x y th vx vy om cth sth Ax Ay h_abs t lx ly rejected | fs alpha act_term | scene[10]
+constexpr int kContFields = SG_CONT_GATHER ? 18 : 28;  // x y th vx vy om cth sth Ax Ay h_abs t (lx ly) rejected | fs alpha act_term | (scene[10])
 constexpr int kEventFields = 25;  // x y th vx vy om h t_old Ax[7] Ay[7] lx ly active
 constexpr uint32_t kPostReached = 1u << 30, kPostDone = 1u << 31, kPostIndex = (1u << 30) - 1;
 
@@ -579,8 +579,7 @@ __device__ __forceinline__ void save_cont(const DevCfg& c, uint32_t* q_idx, doub
     }
 }
 
-// everything else the single-attempt continuation kernel needs, so that it reads coalesced scratch rows
-// instead of gathering the env's state by index
+// the action terms (and, without SG_CONT_GATHER, the scene) next to the integrator state of a continuation record
 template <class TR>
 __device__ __forceinline__ void save_cont_scene(const DevCfg& c, double* scr, uint32_t slot, const EnvRegs<TR>& e,
                                                 const Act& act) {
@@ -1274,7 +1273,7 @@ cont_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ 
             SG_CHK(chk_consume(c, 0, i);)
             EnvRegs<TR> e;
             Act act;
-            load_cont_scene<TR>(c, scr_in, j, i, e, act);  // planets / goal / action terms: coalesced scratch rows, no gather
+            load_cont_scene<TR>(c, scr_in, j, i, e, act);  // action terms from the record; planets / goal gathered from the state block
             bool rejected;
             const uint32_t elapsed0 = c.elapsed[i];
             const double ep_ret0 = c.ep_return[i];
