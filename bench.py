@@ -523,11 +523,23 @@ def run_b200(args):
         rc = L.sg_measure_fp64_peak(local, 300.0, tf.ref)
         fp64_peak = tf.value if rc == 0 else None
         fp64_ach = ALGO_FLOPS_PER_STEP * n / launch_s / 1e12
-        traffic = None
+        traffic, pipe = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch")
+                # whole-step FP64-pipe use in the overlapped state: executed FP64-pipe warp instructions of the three
+                # kernels of one step (ncu counters, profiles/) over the step time measured HERE, against 0.5 warp
+                # instructions per cycle on each of the SM sub-partitions at the SM clock sampled during the run
+                ipp = tj.get("fp64_pipe", {}).get("fp64_pipe_warp_instructions_per_step")
+                props = torch.cuda.get_device_properties(dev)
+                mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                if ipp and n == ENVS_PER_STEP and ENV_ID == "GoalContinuous3P-v0":
+                    peak = props.multi_processor_count * 4 * 0.5 * mhz * 1e6
+                    pipe = {"fp64_pipe_warp_instructions_per_step": ipp, "achieved_per_s": ipp / launch_s, "peak_per_s": peak,
+                            "frac": ipp / launch_s / peak, "sm_mhz": mhz,
+                            "how": "instruction counts from ncu (profiles/traffic.json), step time from this run"}
             except Exception:
                 traffic = None
         line = {
@@ -557,6 +569,7 @@ def run_b200(args):
                                     "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
                                              "frac": (fp64_ach / fp64_peak) if fp64_peak else None},
                                     "note": "all kernels of a step (hot+continuation+tail), from `value`"},
+            "roofline_fp64_pipe_whole_step": pipe,
             "kernel_times": kt,
             "single_handle": single,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -70,6 +70,24 @@ def main():
                "per_kernel": traffic, "algorithmic_bytes_hot_kernel": int(329 * 193121),
                "algorithmic_bytes_whole_step": 86245376},
               open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    # executed FP64-pipe warp instructions per kernel (bench.py: roofline_fp64_pipe_whole_step)
+    import re
+    fp = {}
+    for k in KERNELS:
+        if os.path.exists(dst(f"{k}_dynamic_mix.txt")):
+            m = re.match(r"warps (\d+)\s+executed (\d+)\s+per warp ([\d.]+)\s+fp64-pipe per warp ([\d.]+)",
+                         open(dst(f"{k}_dynamic_mix.txt")).readline())
+            if m:
+                fp[k] = {"warps": int(m.group(1)), "executed_warp_instructions": int(m.group(2)),
+                         "fp64_pipe_warp_instructions": round(float(m.group(4)) * int(m.group(1)))}
+    if len(fp) == len(KERNELS):
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        tj["fp64_pipe"] = {"per_kernel": fp,
+                           "fp64_pipe_warp_instructions_per_step": sum(v["fp64_pipe_warp_instructions"] for v in fp.values()),
+                           "what": "executed FP64-pipe warp instructions (DFMA, DMUL, DADD, DSETP, MUFU.RCP64H / RSQ64H) of the "
+                                   f"three kernels of ONE 262144-env step, ncu source-page counters of profiles/{tag}_* "
+                                   "(tools/ncu_dynamic_mix.py); the pipe issues 0.5 warp instructions per cycle per scheduler"}
+        json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     shutil.copy(src("launches.csv"), dst("launches_final.csv"))
     shutil.copy(src("bench.json"), dst("bench_final.json"))
     if os.path.exists(src("ref.json")):
