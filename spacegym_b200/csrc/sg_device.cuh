@@ -1035,114 +1035,6 @@ __device__ __forceinline__ void rk_attempt(const DevCfg& c, const EnvRegs<TR>& e
     err2 = (ex * ex + ey * ey + evx * evx + evy * evy) * HT(sixth);  // error_norm ** 2
 }
 
-// rk_attempt with the stage forces and the stage headings parked in shared memory (hot kernel, SG_HOT_SMEM_A).
-// The six forces A_0..A_5 (12 doubles) and the five / six rotated headings (10 / 12 doubles) are each written once
-// and read a few times, but held in registers they are live across the whole attempt and are what pins the kernel
-// at 128 registers (4 CTAs per SM); in the lane's own shared-memory column they cost 21 128-bit loads and 12
-// stores per attempt and leave room for a fifth CTA.  A[k * 32] / H[j * 32] are the lane's double2 slots (x, y) /
-// (cos, sin); lanes of a warp sit 16 bytes apart, so the accesses are conflict-free.  The error combination is folded
-// into the same pass over A_0..A_5 as the end-point combination, so every force is loaded once per use site.
-// Arithmetic (order of operations, constants) is that of rk_attempt's default branch: results are bit-identical.
-template <class TR>
-__device__ __forceinline__ void rk_attempt_sm(const DevCfg& c, const EnvRegs<TR>& e, const Integ<TR>& S, double h,
-                                              double2* __restrict__ A, double2* __restrict__ H, double& A6x,
-                                              double& A6y, double& xn, double& yn, double& thn, double& vxn,
-                                              double& vyn, double& omn, double& cn, double& sn, double& err2,
-                                              double (&pdn)[TR::NP], double (&ipdn)[TR::NP]) {
-    const double x = S.x, y = S.y, vx = S.vx, vy = S.vy;
-    const double hh = h * h, ho = h * S.om, ha = hh * S.alpha;
-    const bool small = fabs(ho) + fabs(ha) < 0.5;
-    constexpr int NH = (TR::STEER == STEER_VEL) ? 5 : 6;
-    {
-        double d[6], sd[6], cd[6];
-        d[0] = HT(c2) * ho;
-        d[1] = HT(c3) * ho + HT(cs3) * ha;
-        d[2] = HT(c4) * ho + HT(cs4) * ha;
-        d[3] = HT(c5) * ho + HT(cs5) * ha;
-        d[4] = ho + HT(cs6) * ha;
-        d[5] = ho + HT(cs7) * ha;
-        if (TR::STEER == STEER_VEL && small) {
-            const double dd[3] = {d[0], d[1], d[3]};
-            double s3[3], c3[3];
-            small_sincos_n<3>(dd, true, s3, c3);
-            sd[0] = s3[0]; cd[0] = c3[0];
-            sd[1] = s3[1]; cd[1] = c3[1];
-            sd[3] = s3[2]; cd[3] = c3[2];
-            const double s2 = 2.0 * (s3[0] * c3[0]), c2a = fma(-2.0 * s3[0], s3[0], 1.0);
-            sd[2] = 2.0 * (s2 * c2a);
-            cd[2] = fma(-2.0 * s2, s2, 1.0);
-            sd[4] = fma(sd[2], c3[0], cd[2] * s3[0]);
-            cd[4] = fma(cd[2], c3[0], -(sd[2] * s3[0]));
-            sd[5] = sd[4];
-            cd[5] = cd[4];
-        } else {
-            small_sincos_n<6>(d, small, sd, cd);
-        }
-        thn = S.th + d[5];
-#pragma unroll
-        for (int j = 0; j < NH; ++j)
-            H[j * 32] = make_double2(S.cth * cd[j] - S.sth * sd[j], S.sth * cd[j] + S.cth * sd[j]);
-        // velocity steering: alpha == 0, so d[4] == d[5] bit for bit on either branch and five headings suffice
-    }
-    omn = S.om + h * S.alpha;
-    double2 a0 = make_double2(S.Ax, S.Ay), a1, a2, a3, a4, a5, hd;
-    A[0 * 32] = a0;
-    hd = H[0 * 32];
-    accel(c, e, x + (HT(c2) * h) * vx, y + (HT(c2) * h) * vy, hd.x, hd.y, S.fs, a1.x, a1.y);
-    A[1 * 32] = a1;
-    hd = H[1 * 32];
-    accel(c, e, x + (HT(c3) * h) * vx + hh * (HT(ab31) * a0.x), y + (HT(c3) * h) * vy + hh * (HT(ab31) * a0.y), hd.x, hd.y,
-          S.fs, a2.x, a2.y);
-    A[2 * 32] = a2;
-    a0 = A[0 * 32];
-    a1 = A[1 * 32];
-    hd = H[2 * 32];
-    accel(c, e, x + (HT(c4) * h) * vx + hh * (HT(ab41) * a0.x + HT(ab42) * a1.x),
-          y + (HT(c4) * h) * vy + hh * (HT(ab41) * a0.y + HT(ab42) * a1.y), hd.x, hd.y, S.fs, a3.x, a3.y);
-    A[3 * 32] = a3;
-    a0 = A[0 * 32];
-    a1 = A[1 * 32];
-    a2 = A[2 * 32];
-    hd = H[3 * 32];
-    accel(c, e, x + (HT(c5) * h) * vx + hh * (HT(ab51) * a0.x + HT(ab52) * a1.x + HT(ab53) * a2.x),
-          y + (HT(c5) * h) * vy + hh * (HT(ab51) * a0.y + HT(ab52) * a1.y + HT(ab53) * a2.y), hd.x, hd.y, S.fs, a4.x, a4.y);
-    A[4 * 32] = a4;
-    a0 = A[0 * 32];
-    a1 = A[1 * 32];
-    a2 = A[2 * 32];
-    a3 = A[3 * 32];
-    hd = H[4 * 32];
-    accel(c, e, x + h * vx + hh * (HT(ab61) * a0.x + HT(ab62) * a1.x + HT(ab63) * a2.x + HT(ab64) * a3.x),
-          y + h * vy + hh * (HT(ab61) * a0.y + HT(ab62) * a1.y + HT(ab63) * a2.y + HT(ab64) * a3.y), hd.x, hd.y, S.fs, a5.x,
-          a5.y);
-    A[5 * 32] = a5;
-    a0 = A[0 * 32];
-    a1 = A[1 * 32];
-    a2 = A[2 * 32];
-    a3 = A[3 * 32];
-    a4 = A[4 * 32];
-    xn = x + h * vx + hh * (HT(bb1) * a0.x + HT(bb2) * a1.x + HT(bb3) * a2.x + HT(bb4) * a3.x + HT(bb5) * a4.x);
-    yn = y + h * vy + hh * (HT(bb1) * a0.y + HT(bb2) * a1.y + HT(bb3) * a2.y + HT(bb4) * a3.y + HT(bb5) * a4.y);
-    vxn = vx + h * (HT(b1) * a0.x + HT(b3) * a2.x + HT(b4) * a3.x + HT(b5) * a4.x + HT(b6) * a5.x);
-    vyn = vy + h * (HT(b1) * a0.y + HT(b3) * a2.y + HT(b4) * a3.y + HT(b5) * a4.y + HT(b6) * a5.y);
-    double ex = hh * (HT(eb1) * a0.x + HT(eb2) * a1.x + HT(eb3) * a2.x + HT(eb4) * a3.x + HT(eb5) * a4.x + HT(eb6) * a5.x);
-    double ey = hh * (HT(eb1) * a0.y + HT(eb2) * a1.y + HT(eb3) * a2.y + HT(eb4) * a3.y + HT(eb5) * a4.y + HT(eb6) * a5.y);
-    // e7 * A_6 is the last term of the velocity error rows in rk_attempt too: the partial sums below are its prefix
-    double pvx = HT(e1) * a0.x + HT(e3) * a2.x + HT(e4) * a3.x + HT(e5) * a4.x + HT(e6) * a5.x;
-    double pvy = HT(e1) * a0.y + HT(e3) * a2.y + HT(e4) * a3.y + HT(e5) * a4.y + HT(e6) * a5.y;
-    hd = H[(NH - 1) * 32];  // the end point's heading (stage 7 == stage 6 heading in velocity steering)
-    cn = hd.x;
-    sn = hd.y;
-    accel_pd<TR>(c, e, xn, yn, cn, sn, S.fs, A6x, A6y, pdn, ipdn);
-    double evx = h * (pvx + HT(e7) * A6x);
-    double evy = h * (pvy + HT(e7) * A6y);
-    ex *= fast_rcp(HT(atol) + sel_max(fabs(x), fabs(xn)) * HT(rtol));
-    ey *= fast_rcp(HT(atol) + sel_max(fabs(y), fabs(yn)) * HT(rtol));
-    evx *= fast_rcp(HT(atol) + sel_max(fabs(vx), fabs(vxn)) * HT(rtol));
-    evy *= fast_rcp(HT(atol) + sel_max(fabs(vy), fabs(vyn)) * HT(rtol));
-    err2 = (ex * ex + ey * ey + evx * evx + evy * evy) * HT(sixth);
-}
-
 __device__ __forceinline__ double min_step_at(double t) {  // 10 * |nextafter(t, inf) - t|, scipy:rk.py:119
     return 10 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
 }

@@ -691,26 +691,6 @@ enum { KIND_DONE = 0, KIND_CONT = 1, KIND_EVENT = 2, KIND_FINISH = 3, KIND_CONT_
 #ifndef SG_TAIL_GRID
 #define SG_TAIL_GRID 1
 #endif
-// SG_HOT_SMEM_A (option, off): stage forces and stage headings of the attempt parked in shared memory instead of
-// registers, to make room for a fifth CTA per SM.  Measured (r2 dev runs, 16 x 262144 envs / one handle): 4 CTAs per SM
-// 5.95e9 / 4.27e9 env-steps/s (no spills) against 5.91e9 / 4.26e9 of the same build without it; 5 CTAs per SM
-// (-DSG_HOT_MINB=5: 96 registers, 104 B of spills left; with the planets parked as well or the goal re-read after the
-// attempt ptxas spills MORE, 176-184 B) 5.78e9 / 4.13e9, hot kernel 39.4 vs 38.2 us: a fifth warp per scheduler does not
-// pay for its spills — the same outcome as the 64-thread / 112- and 96-register builds of round 1.
-// Shared memory of one warp of the hot kernel, in doubles.  [0, R0): the warp's 32 observation rows
-// (epilogue) and, before that, the lanes' stage headings (NH double2 columns); [R0, R0 + 7 * 64): the stage forces
-// A_0..A_6 as double2 columns (they outlive the epilogue on event lanes, so they do not share the rows' space).
-#ifndef SG_HOT_SMEM_A
-#define SG_HOT_SMEM_A 0
-#endif
-
-template <class TR, typename OT>
-struct HotWarpSmem {
-    static constexpr int NH = (TR::STEER == STEER_VEL) ? 5 : 6;
-    static constexpr int ROWS = (32 * TR::D * (int)sizeof(OT) + 15) / 16 * 2;  // doubles, 16-byte granules
-    static constexpr int R0 = ROWS > NH * 64 ? ROWS : NH * 64;
-    static constexpr int WORDS = R0 + 7 * 64;
-};
 // One chunk of kBlock envs through the common path.  `publish` = true (fused persistent kernel): a
 // continuation entry becomes visible to the in-kernel consumers by the release of its index word.
 // ---- staged inputs of the persistent hot kernel ---------------------------------------------------------
@@ -796,15 +776,9 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
                                           OT* __restrict__ obs, double* __restrict__ reward,
                                           uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                           long long block_first, OT* sobs, double (&st)[4], bool publish,
-                                          const Stage<TR>* stage = nullptr, double* stash = nullptr,
-                                          double* wsm = nullptr) {
+                                          const Stage<TR>* stage = nullptr, double* stash = nullptr) {
     constexpr int D = TR::D;
-    // SG_HOT_SMEM_A (hot_kernel only): wsm = the warp's shared-memory region (HotWarpSmem): observation rows /
-    // stage headings, then the stage forces; `sobs` is then the warp's row block, not the CTA's
-    constexpr bool SMA = SG_HOT_SMEM_A && !STAGED;
-    OT* const my_row = SMA ? reinterpret_cast<OT*>(wsm) + (threadIdx.x & 31) * D : sobs + threadIdx.x * D;
-    double2* const smA = reinterpret_cast<double2*>(wsm + HotWarpSmem<TR, OT>::R0) + (threadIdx.x & 31);
-    double2* const smH = reinterpret_cast<double2*>(wsm) + (threadIdx.x & 31);
+    OT* const my_row = sobs + threadIdx.x * D;
     const long long i = block_first + threadIdx.x;
     const bool valid = i < c.n;
     int kind = KIND_DONE;
@@ -848,8 +822,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
         h = t_new;
         S.h_abs = fabs(h);
         double xn, yn, thn, vxn, vyn, omn, cn, sn, err2, ipd[TR::NP];
-        if (SMA) rk_attempt_sm<TR>(c, e, S, h, smA, smH, Ax[6], Ay[6], xn, yn, thn, vxn, vyn, omn, cn, sn, err2, pd, ipd);
-        else rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2, pd, ipd);
+        rk_attempt<TR>(c, e, S, h, Ax, Ay, xn, yn, thn, vxn, vyn, omn, cn, sn, err2, pd, ipd);
         if (!controller(err2, rejected, t_new < c.T, S.h_abs)) {
             kind = KIND_CONT_REJECTED;  // the attempt loop is resumed from the same state with the smaller step
         } else {
@@ -862,9 +835,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
                 // row of the observation staging area, not in registers across the epilogue of the finished lanes:
                 // 48 bytes of spills -> none at 128 registers (+2 %).  Staging the continuation lanes' integrator
                 // state the same way measured slower.  Needs a 14-double row: f64 observations of Goal 3P / 4P.
-                if (SMA) {
-                    smA[6 * 32] = make_double2(Ax[6], Ay[6]);  // A_0..A_5 are there already
-                } else if (sizeof(OT) == 8 && D >= 14) {
+                if (sizeof(OT) == 8 && D >= 14) {
                     double* r = reinterpret_cast<double*>(sobs) + threadIdx.x * D;
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
@@ -943,14 +914,7 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
         if (publish) st_release(c.q_cont + s_cont, (uint32_t)i);  // scratch row visible before "ready"
     }
     if (kind == KIND_EVENT) {
-        if (SMA) {
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const double2 a = smA[k * 32];
-                Ax[k] = a.x;
-                Ay[k] = a.y;
-            }
-        } else if (sizeof(OT) == 8 && D >= 14) {
+        if (sizeof(OT) == 8 && D >= 14) {
             const double* r = reinterpret_cast<const double*>(sobs) + threadIdx.x * D;
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
@@ -963,38 +927,8 @@ __device__ __forceinline__ void hot_chunk(const DevCfg& c, const float* __restri
     if (need_post) c.q_post[s_post] = (uint32_t)i | (reached ? kPostReached : 0u) | (done ? kPostDone : 0u);
     if (obs) {  // rows of queued envs are rewritten by the later kernels
         __syncwarp();
-        if (SMA) flush_obs_warp<OT, D>(reinterpret_cast<const OT*>(wsm) - 32 * (threadIdx.x >> 5) * D, obs, block_first, c.n);
-        else flush_obs_warp<OT, D>(sobs, obs, block_first, c.n);
+        flush_obs_warp<OT, D>(sobs, obs, block_first, c.n);
     }
-}
-
-// DRAM -> L2 prefetch of the input rows of a LATER chunk of the grid (the CTA that will take over this CTA's slot about
-// one wave from now): a CTA's first instruction that needs its inputs waits for them (12 % of a warp's life in the
-// ncu capture with cold caches), and with four warps per scheduler nothing covers that wait.  One 128-byte line per
-// thread and row group; rows already in L2 (one handle stepped back to back) make this a no-op.
-// Measured (r2 dev runs): 5.66e9 / 5.67e9 env-steps/s with a distance of 592 / 296 CTAs against 5.74e9 without, hot
-// kernel 38.1 / 37.2 vs 36.4 us: the prefetch instructions cost more than the shorter wait returns.  Off.
-#ifndef SG_HOT_PREFETCH
-#define SG_HOT_PREFETCH 0
-#endif
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <class TR>
-__device__ __forceinline__ void prefetch_chunk_l2(const DevCfg& c, const float* __restrict__ actions, long long first) {
-    if (first + kBlock > c.n) return;
-    // 8 lines of 16 doubles per row of the chunk; thread t takes line (t & 7) of rows (t >> 3), (t >> 3) + 16, ...
-    constexpr int ROWS = 6 + (TR::TASK == TASK_GOAL ? 2 * TR::NP + 2 : (TR::TASK == TASK_KEPLER ? 2 : 0)) + 1;
-    const long long n = c.stride;
-    const int line = threadIdx.x & 7;
-    for (int r = threadIdx.x >> 3; r < ROWS; r += kBlock / 8) {
-        const double* row;
-        if (r < 6) row = c.ship + r * n;
-        else if (r == ROWS - 1) row = c.ep_return;
-        else if (TR::TASK == TASK_GOAL) row = (r < 6 + 2 * TR::NP) ? c.planets + (r - 6) * n : c.goal + (r - 6 - 2 * TR::NP) * n;
-        else row = c.orbit + (r - 6) * n;
-        prefetch_l2(row + first + 16 * line);
-    }
-    if (threadIdx.x < 4) prefetch_l2(c.elapsed + first + 32 * threadIdx.x);
-    else if (threadIdx.x < 12 && actions) prefetch_l2(actions + 2 * first + 32 * (threadIdx.x - 4));
 }
 
 #ifdef SG_HOT_MAXREG  // experiment: register cap independent of the CTA count ptxas derives it from
@@ -1006,23 +940,13 @@ template <class TR, typename OT>
 __global__ void SG_HOT_BOUNDS
 hot_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__ obs, double* __restrict__ reward,
            uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out) {
-#if SG_HOT_SMEM_A
-    __shared__ __align__(16) double wsm_all[(kBlock / 32) * HotWarpSmem<TR, OT>::WORDS];
-    double* const wsm = wsm_all + (threadIdx.x >> 5) * HotWarpSmem<TR, OT>::WORDS;
-    OT* const sobs = nullptr;
-#else
     __shared__ __align__(16) OT sobs[kBlock * TR::D];
-    double* const wsm = nullptr;
-#endif
     __shared__ double stash[4 * kBlock];
     pdl_wait();  // the previous step's tail kernel has written the state and emptied the queues
-#if SG_HOT_PREFETCH > 0
-    prefetch_chunk_l2<TR>(c, actions, ((long long)blockIdx.x + SG_HOT_PREFETCH) * kBlock);
-#endif
     const unsigned long long step0 = *reinterpret_cast<const unsigned long long*>(c.q_counts + 4);
     double st[4] = {0, 0, 0, 0};
     hot_chunk<TR, OT>(c, actions, step0, obs, reward, done_out, trunc_out, (long long)blockIdx.x * kBlock, sobs, st, false,
-                      nullptr, stash, wsm);
+                      nullptr, stash);
     warp_stats_flush(c, st);
 }
 
