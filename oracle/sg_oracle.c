@@ -1079,6 +1079,26 @@ void so_engine_reset(const so_config* cfg, so_env* envs, int64_t n, uint64_t see
     }
 }
 
+/* env.reset() on a LIVE batch (include/spacegym_b200.h: sg_reset with a mask; spaceship_env.py:59-66 called again
+ * after an episode): the masked envs (mask == NULL: all) restart from the next Philox block of their own stream, as
+ * the auto-reset inside so_engine_step does; the others keep their state and report their current observation. */
+void so_engine_reset_live(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed,
+                          int64_t first_env_index, const uint8_t* mask, double* obs, int n_threads) {
+    int D = so_obs_dim(cfg);
+    n_threads = pick_threads(n_threads);
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        so_env* e = &envs[i];
+        if (!mask || mask[i]) {
+            so_draws d;
+            so_draws_philox(&d, seed, (uint64_t)(first_env_index + i), e->rng_ctr);
+            so_reset(cfg, e, &d);
+            e->rng_ctr = d.ctr;
+        }
+        if (obs) so_make_obs(cfg, e, obs + i * D);
+    }
+}
+
 void so_engine_step(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed,
                     int64_t first_env_index, uint64_t step0, int K, const float* actions,
                     int auto_reset, double* obs, double* reward, uint8_t* done,

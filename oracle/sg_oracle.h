@@ -134,6 +134,8 @@ void so_random_action(uint64_t seed, uint64_t env_index, uint64_t step, int disc
  * stats[4] += {sum return, sum length, episodes, goals}. n_threads <= 0: all cores. */
 void so_engine_reset(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed,
                      int64_t first_env_index, double* obs, int n_threads);
+void so_engine_reset_live(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed,
+                          int64_t first_env_index, const uint8_t* mask, double* obs, int n_threads);
 void so_engine_step(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed,
                     int64_t first_env_index, uint64_t step0, int K, const float* actions,
                     int auto_reset, double* obs, double* reward, uint8_t* done,

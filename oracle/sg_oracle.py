@@ -92,12 +92,14 @@ def lib():
         L.so_random_action.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, fp]
         L.so_engine_reset.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p,
                                       C.c_int]
+        L.so_engine_reset_live.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_int]
         L.so_engine_step.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_uint64,
                                      C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int]
         for f in (L.so_rhs, L.so_config_finalize, L.so_make_obs, L.so_reset, L.so_find_new_goal,
                   L.so_philox4x32_10, L.so_draws_philox, L.so_draws_tape, L.so_random_action,
-                  L.so_engine_reset, L.so_engine_step):
+                  L.so_engine_reset, L.so_engine_reset_live, L.so_engine_step):
             f.restype = None
         _lib = L
     return _lib
@@ -166,6 +168,15 @@ class Engine:
         lib().so_engine_reset(C.byref(self.cfg), _vp(self.envs), self.n, self.seed, self.first, _vp(obs),
                               self.n_threads)
         self.step_count = 0
+        return obs
+
+    def reset_live(self, mask=None):
+        """env.reset() of a batch that is already running (sg_reset): masked envs (None: all) restart from the next
+        block of their own random stream; returns the observation of every env."""
+        obs = np.zeros((self.n, self.D))
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().so_engine_reset_live(C.byref(self.cfg), _vp(self.envs), self.n, self.seed, self.first, _vp(m), _vp(obs),
+                                   self.n_threads)
         return obs
 
     def step(self, actions=None, K=1, auto_reset=True, want_obs=True):

@@ -206,3 +206,68 @@ def test_non_finite_state_terminates_and_is_flagged(mode):
     assert torch.equal(o[~torch.as_tensor(bad, device=o.device)], o2[~torch.as_tensor(bad, device=o.device)])
     env.close()
     ref.close()
+
+
+def test_single_env_adapter_runs_the_reference_loop(oracle):
+    """SpaceEnv: the reference's own call pattern (gym.make -> seed -> reset -> step ... if done: reset) for ONE env,
+    numpy in / numpy and python scalars out, TimeLimit info key, action asserts, rgb_array render — in lockstep with the
+    oracle twin stepped without auto-reset (BASELINE configs[0] shape: GoalContinuous2P-v0, one env)."""
+    cfg = oracle_cfg(oracle, "goal2p", max_episode_steps=40)
+    eng = oracle.Engine(cfg, 1, seed=3)
+    env = sg.make_single("GoalContinuous2P-v0", seed=11, max_episode_steps=40)
+    with pytest.raises(AssertionError):
+        env.step(np.zeros(2, dtype=np.float32))  # before the first reset (gym TimeLimit)
+    assert env.seed(3) == [3]
+    assert env.observation_space.shape == (13,) and env.action_space.shape == (2,)
+    obs = env.reset()
+    assert obs.shape == (13,) and close(obs, eng.reset()[0]).all()
+    rng = np.random.RandomState(8)
+    episodes = truncated = 0
+    for t in range(400):
+        a = rng.uniform(-1, 1, size=2).astype(np.float32)
+        o, r, d, info = env.step(a)
+        o_o, r_o, d_o, tr_o = eng.step(a[None, None], auto_reset=False)
+        assert isinstance(r, float) and isinstance(d, bool) and o.shape == (13,)
+        assert close(o, o_o[0]).all() and close(r, r_o[0][0]) and d == bool(d_o[0][0])
+        assert ("TimeLimit.truncated" in info) == bool(tr_o[0][0])
+        truncated += int("TimeLimit.truncated" in info)
+        if d:
+            episodes += 1
+            assert close(env.reset(), eng.reset_live()[0]).all()
+    assert episodes >= 8 and truncated >= 1
+    with pytest.raises(AssertionError):
+        env.step(np.array([2.0, 0.0], dtype=np.float32))  # outside Box(-1, 1): spaceship_env.py:71
+    frame = env.render()
+    assert frame.ndim == 3 and frame.shape[2] == 3 and frame.dtype == np.uint8 and frame.any()
+    assert close(env.vector_field(np.zeros(2, dtype=np.float32))[:2], env.get_state()["ship"][0, 3:5].cpu().numpy()).all()
+    env.close()
+
+
+@pytest.mark.parametrize("case,env_id", [("goal3p", "GoalContinuous3P-v0"), ("kepler_random", "KeplerRandomOrbits-v0")])
+def test_masked_reset_of_a_live_batch_matches_the_oracle(oracle, case, env_id):
+    """sg_reset on a running batch (the reference's `if done: env.reset()` for a subset of envs): the masked envs restart
+    from the next block of their own stream, the others keep their state; observation rows and the whole state against
+    the oracle twin's live reset, then stepping goes on in lockstep."""
+    n, seed = 1000, 21
+    cfg = oracle_cfg(oracle, case)
+    eng = oracle.Engine(cfg, n, seed=seed)
+    from helpers import engine_kwargs
+    _, kw = engine_kwargs(case)
+    env = sg.make(env_id, n, seed=seed, **kw)
+    assert close(env.reset().cpu().numpy(), eng.reset()).all()
+    rng = np.random.RandomState(4)
+    for rep in range(3):
+        for _ in range(5):
+            a = random_actions(rng, 1, n, bool(cfg.discrete))
+            eng.step(a)
+            env.step(to_dev(a[0]))
+        mask = (rng.uniform(size=n) < 0.3).astype(np.uint8)
+        obs_d = env.reset(torch.as_tensor(mask))  # a CPU mask is moved to the device by the host layer
+        obs_o = eng.reset_live(mask)
+        assert close(obs_d.cpu().numpy(), obs_o).all()
+        assert compare_engine_to_oracle(cfg, env.get_state(), eng.envs).all()
+    a = random_actions(rng, 1, n, bool(cfg.discrete))
+    o_o, r_o, d_o, _ = eng.step(a)
+    o_d, r_d, d_d, _ = env.step(to_dev(a[0]))
+    assert close(o_d.cpu().numpy(), o_o).all() and close(r_d.cpu().numpy(), r_o[0]).all()
+    env.close()

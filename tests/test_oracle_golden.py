@@ -118,3 +118,22 @@ def test_survey_known_answers(oracle):
     assert np.allclose(r["state1"], [-1.9064314792303383, -0.5947628607702902, 3.6632500001825394,
                                       -0.08369974277110878, 0.0795363218657613, -0.3499999947845935], rtol=0, atol=1e-14)
     assert abs(r["reward"] - 0.00664986264606105) < 1e-15
+
+
+def test_oracle_live_reset_continues_each_env_stream(oracle):
+    """so_engine_reset_live (the twin of sg_reset on a running batch): masked envs restart from the next block of their
+    own Philox stream — a second reset does not repeat the first placement — and unmasked envs keep their state."""
+    cfg = oracle.config_from_id("GoalContinuous3P-v0")
+    eng = oracle.Engine(cfg, 64, seed=2)
+    o0 = eng.reset()
+    ctr0 = eng.envs["rng_ctr"].copy()
+    mask = np.zeros(64, dtype=np.uint8)
+    mask[::3] = 1
+    before = eng.envs.copy()
+    o1 = eng.reset_live(mask)
+    m = mask.astype(bool)
+    assert (eng.envs["rng_ctr"][m] > ctr0[m]).all() and (eng.envs["rng_ctr"][~m] == ctr0[~m]).all()
+    assert (o1[~m] == o0[~m]).all() and (np.abs(o1[m] - o0[m]).max(axis=1) > 0).all()
+    assert (eng.envs["y"][~m] == before["y"][~m]).all() and (eng.envs["elapsed"][m] == 0).all()
+    # a fresh engine reset restarts the streams: same placement as the very first reset
+    assert (eng.reset() == o0).all()
