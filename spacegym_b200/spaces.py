@@ -23,6 +23,15 @@ class Box:
         return bool(np.can_cast(x.dtype, self.dtype) and x.shape == self.shape
                     and np.all(x >= self.low) and np.all(x <= self.high))
 
+    def sample(self, rng=None):
+        """gym.spaces.Box.sample for the bounded case (the action space); unbounded entries draw a standard normal."""
+        rng = np.random if rng is None else rng
+        lo, hi = np.asarray(self.low, dtype=np.float64), np.asarray(self.high, dtype=np.float64)
+        bounded = np.isfinite(lo) & np.isfinite(hi)
+        u = rng.uniform(size=self.shape)
+        x = np.where(bounded, np.where(bounded, lo, 0.0) + u * np.where(bounded, hi - lo, 0.0), rng.standard_normal(self.shape))
+        return x.astype(self.dtype)
+
 
 @dataclass(frozen=True)
 class Discrete:
@@ -32,3 +41,7 @@ class Discrete:
 
     def contains(self, x):
         return isinstance(x, (int, np.integer)) and 0 <= int(x) < self.n
+
+    def sample(self, rng=None):
+        rng = np.random if rng is None else rng
+        return int(rng.randint(self.n))

@@ -127,3 +127,19 @@ def test_build_script_knows_every_part():
     for k in range(1, build.N_PARTS):
         assert re.search(rf"#elif SG_PART == {k}\ntemplate void launch_np<", src), k
     assert f"#elif SG_PART == {build.N_PARTS}" not in src
+
+
+def test_spaces_sample_and_contain():
+    """Box / Discrete stand-ins for the gym spaces the reference builds (spaceship_env.py:102-111,183-214)."""
+    import numpy as np
+    from spacegym_b200 import spaces
+    box = spaces.Box(-np.ones(2, dtype=np.float32), np.ones(2, dtype=np.float32))
+    rng = np.random.RandomState(0)
+    for _ in range(50):
+        x = box.sample(rng)
+        assert x.dtype == np.float32 and box.contains(x)
+    assert not box.contains(np.array([1.5, 0.0], dtype=np.float32)) and not box.contains(np.zeros(3, dtype=np.float32))
+    hi = np.array([1.0, np.inf], dtype=np.float32)
+    assert np.isfinite(spaces.Box(-hi, hi).sample(rng)).all()
+    d = spaces.Discrete(6)
+    assert all(d.contains(d.sample(rng)) for _ in range(50)) and not d.contains(6) and not d.contains(1.0)
