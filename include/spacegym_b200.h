@@ -195,6 +195,13 @@ int sg_set_step_count(sg_env* env, uint64_t steps);
 /* env.seed(seed) (spaceship_env.py:92-94, goal.py:74-77): re-key every env's random streams and restart their
  * counters (and the step counter); the next reset / step draws from the new streams.  Synchronises the device. */
 int sg_reseed(sg_env* env, uint64_t seed);
+/* Terminal observations under auto-reset.  The reference's loop sees the last observation of an episode because the
+ * caller resets (spaceship_env.py:68-78 returns it with done = True); with auto_reset the step returns the reset
+ * observation instead (gym 0.21 SyncVectorEnv).  d_term_obs: [N][D] rows of the dtype of the step's d_obs (16-byte
+ * aligned), or NULL to turn it off.  Every sg_step call that writes an observation (K = 1, or the last of K steps) then
+ * also writes, for each env that restarted in that step, the observation of the state its episode ended in (terminal event or
+ * TimeLimit); rows of other envs are not touched.  Synchronises the device. */
+int sg_set_terminal_obs(sg_env* env, void* d_term_obs);
 int64_t sg_kernel_launches(const sg_env* env);       /* kernels launched by this handle */
 /* Measurement aid, active when the handle was created with SG_TIMING=1 in the environment (sg_step then
  * synchronises inside every step): out[0..2] = mean milliseconds of the {hot, continuation, tail} kernels per

@@ -1103,6 +1103,16 @@ void so_engine_step(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed
                     int64_t first_env_index, uint64_t step0, int K, const float* actions,
                     int auto_reset, double* obs, double* reward, uint8_t* done,
                     uint8_t* truncated, double* stats, int n_threads) {
+    so_engine_step_term(cfg, envs, n, seed, first_env_index, step0, K, actions, auto_reset, obs, reward, done, truncated,
+                        stats, NULL, n_threads);
+}
+
+/* so_engine_step that also reports, for every env that restarted in the LAST of the K steps, the observation of the
+ * state its episode ended in (include/spacegym_b200.h: sg_set_terminal_obs); rows of other envs are not touched. */
+void so_engine_step_term(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed,
+                         int64_t first_env_index, uint64_t step0, int K, const float* actions,
+                         int auto_reset, double* obs, double* reward, uint8_t* done,
+                         uint8_t* truncated, double* stats, double* term_obs, int n_threads) {
     int D = so_obs_dim(cfg);
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     n_threads = pick_threads(n_threads);
@@ -1143,6 +1153,7 @@ void so_engine_step(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed
                 s1 += e->elapsed;
                 s2 += 1;
                 if (auto_reset) { /* gym.vector SyncVectorEnv (0.21): obs := reset obs */
+                    if (term_obs && k == K - 1) memcpy(term_obs + i * D, o, sizeof(double) * D);
                     d.have_u = d.have_n = 0; /* a reset starts on a fresh Philox block */
                     so_reset(cfg, e, &d);
                     so_make_obs(cfg, e, o);

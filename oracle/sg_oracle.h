@@ -141,6 +141,11 @@ void so_engine_step(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed
                     int auto_reset, double* obs, double* reward, uint8_t* done,
                     uint8_t* truncated, double* stats, int n_threads);
 
+void so_engine_step_term(const so_config* cfg, so_env* envs, int64_t n, uint64_t seed,
+                         int64_t first_env_index, uint64_t step0, int K, const float* actions,
+                         int auto_reset, double* obs, double* reward, uint8_t* done,
+                         uint8_t* truncated, double* stats, double* term_obs, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

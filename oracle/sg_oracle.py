@@ -97,6 +97,10 @@ def lib():
         L.so_engine_step.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_uint64,
                                      C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int]
+        L.so_engine_step_term.argtypes = [C.POINTER(Config), C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_uint64,
+                                          C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int]
+        L.so_engine_step_term.restype = None
         for f in (L.so_rhs, L.so_config_finalize, L.so_make_obs, L.so_reset, L.so_find_new_goal,
                   L.so_philox4x32_10, L.so_draws_philox, L.so_draws_tape, L.so_random_action,
                   L.so_engine_reset, L.so_engine_reset_live, L.so_engine_step):
@@ -179,7 +183,8 @@ class Engine:
                                    self.n_threads)
         return obs
 
-    def step(self, actions=None, K=1, auto_reset=True, want_obs=True):
+    def step(self, actions=None, K=1, auto_reset=True, want_obs=True, term_obs=None):
+        """term_obs: float64 [n, D] array that receives the terminal observation of envs restarting in the last step."""
         if actions is not None:
             actions = np.ascontiguousarray(actions, dtype=np.float32)
             if actions.ndim == 2:
@@ -189,8 +194,8 @@ class Engine:
         rew = np.zeros((K, self.n))
         done = np.zeros((K, self.n), dtype=np.uint8)
         trunc = np.zeros((K, self.n), dtype=np.uint8)
-        lib().so_engine_step(C.byref(self.cfg), _vp(self.envs), self.n, self.seed, self.first, self.step_count, K,
-                             _vp(actions), int(auto_reset), _vp(obs), _vp(rew), _vp(done), _vp(trunc),
-                             _vp(self.stats), self.n_threads)
+        lib().so_engine_step_term(C.byref(self.cfg), _vp(self.envs), self.n, self.seed, self.first, self.step_count, K,
+                                  _vp(actions), int(auto_reset), _vp(obs), _vp(rew), _vp(done), _vp(trunc),
+                                  _vp(self.stats), _vp(term_obs), self.n_threads)
         self.step_count += K
         return obs, rew, done, trunc

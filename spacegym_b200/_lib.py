@@ -42,7 +42,7 @@ class SgHostLayout(C.Structure):
 EXPORTS = [
     "sg_config_from_id", "sg_config_finalize", "sg_obs_dim", "sg_state_layout", "sg_create", "sg_destroy",
     "sg_last_error", "sg_get_layout", "sg_state_ptr", "sg_reset", "sg_step", "sg_reset_host", "sg_step_host", "sg_step_host_async", "sg_host_wait",
-    "sg_host_block_layout", "sg_step_host_block_async", "sg_reseed",
+    "sg_host_block_layout", "sg_step_host_block_async", "sg_reseed", "sg_set_terminal_obs",
     "sg_vector_field", "sg_stats", "sg_stats_reset", "sg_step_count", "sg_set_step_count", "sg_kernel_launches",
     "sg_measure_fp64_peak", "sg_version", "sg_debug_kernel_times", "sg_debug_queue_check",
 ]
@@ -82,6 +82,7 @@ def lib():
     L.sg_host_block_layout.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SgHostLayout)]
     L.sg_step_host_block_async.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
     L.sg_reseed.argtypes = [vp, C.c_uint64]
+    L.sg_set_terminal_obs.argtypes = [vp, vp]
     L.sg_debug_queue_check.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.sg_vector_field.argtypes = [vp, vp, vp, vp]
     L.sg_stats.argtypes = [vp, C.POINTER(C.c_double), vp]

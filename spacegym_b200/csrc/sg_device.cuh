@@ -273,6 +273,7 @@ struct DevCfg {
     unsigned long long seed;
     int max_episode_steps, randomize, auto_reset, rows, cols;
     int pack_flags;  // 1: done_out holds done | truncated << 1 in one byte per env (host result block), trunc_out unused
+    void* term_obs;  // [N][D] rows of the step's observation dtype, or NULL: terminal observation of envs that restart in the step
 #ifdef SG_CHECK_QUEUES
     // -DSG_CHECK_QUEUES (debug build, tests/test_gpu_queue_check.py): device-side invariants of the split step's work
     // queues, counted instead of trapped.  chk_err[k]: 0 queue counters not zero when a step starts, 1 queue slot >=

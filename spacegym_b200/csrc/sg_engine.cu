@@ -1441,12 +1441,19 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
                 commit_state<TR>(e, x, y, th, vx, vy, om, status);
                 double gd[TR::NEV], pd[TR::NP], ipd[TR::NP];
                 event_values_inv<TR>(c, e, e.x, e.y, e.om, gd, pd, ipd);
-                const bool want_row = obs && !c.auto_reset;  // with auto-reset the reset observation replaces it
+                // with auto-reset the reset observation replaces the terminal one in `obs`; the terminal row then goes
+                // to the optional terminal-observation buffer (sg_set_terminal_obs)
+                OT* const row_dst = c.auto_reset ? reinterpret_cast<OT*>(c.term_obs) : obs;
+                const bool want_row = obs && row_dst;
                 double sn = 0, cs = 1;
                 if (want_row) sincos_cold(e.th, &sn, &cs);
                 OT row[TR::D];
                 // finish_env without the state stores an auto-reset would overwrite anyway
                 if (want_row) make_obs_inv<TR, OT>(c, e, cs, sn, ipd, row);
+                if (want_row && c.auto_reset) {
+#pragma unroll
+                    for (int k = 0; k < TR::D; ++k) row_dst[i * TR::D + k] = row[k];
+                }
                 double r;
                 bool reached = false;
                 if (TR::TASK == TASK_GOAL) {
@@ -1542,6 +1549,13 @@ tail2_kernel(const DevCfg c, const float* __restrict__ actions, OT* __restrict__
                 if (TR::TILED) store_tiles(c, i, t, true);
                 c.elapsed[i] = 0;
                 c.ep_return[i] = 0.0;
+                if (obs && c.term_obs && j >= n_event) {
+                    // an env that hit its TimeLimit was finished by the hot / continuation kernel, which wrote its
+                    // terminal observation into `obs`: keep that row before the reset observation replaces it
+                    OT* t = reinterpret_cast<OT*>(c.term_obs);
+#pragma unroll
+                    for (int k = 0; k < TR::D; ++k) t[i * TR::D + k] = obs[i * TR::D + k];
+                }
                 if (obs) {
                     double sn, cs;
                     sincos_2pi(e.th, sn, cs);
@@ -1712,6 +1726,7 @@ struct sg_env {
     cudaStream_t hi_stream;
     cudaEvent_t ev_hot, ev_tail;
     int use_priority, use_fused, use_cont1, use_staged;
+    void* term_obs = nullptr;  // sg_set_terminal_obs: [N][D] rows of the observation dtype of the step calls
     int use_pdl;      // SG_PDL (default 1): programmatic dependent launch along the kernel chain
     int tail_mode;    // SG_TAIL: 2 (default) = two-role latency-first tail kernel, 1 = the serial round-1 form
     int tail_grid;    // SG_TAIL_CTAS: CTAs per SM of the tail kernel's grid (32 queue entries per CTA and sweep)
@@ -2278,6 +2293,27 @@ extern "C" int sg_reseed(sg_env* h, uint64_t seed) {
     return SG_OK;
 }
 
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// Terminal observations under auto-reset (gym.vector-style trainers bootstrap from them when an episode is truncated by
+// the TimeLimit): rows [N][D] of the dtype of the step's d_obs.  Every step call that writes an observation also writes,
+// for each env that restarted in that step, the observation of the state its episode ended in; rows of other envs are
+// left as they are.  NULL turns it off.  Written by the tail kernel only (terminal events: computed there; TimeLimit:
+// the row the hot / continuation kernel wrote, saved before the reset observation replaces it).
+extern "C" int sg_set_terminal_obs(sg_env* h, void* d_term_obs) {
+    if (!h) return SG_ERR_INVALID;
+    if (d_term_obs && !aligned16(d_term_obs)) return fail(h, SG_ERR_INVALID, "sg_set_terminal_obs: buffer must be 16-byte aligned");
+    SG_CUDA(h, cudaSetDevice(h->device));
+    SG_CUDA(h, cudaDeviceSynchronize());
+    h->term_obs = d_term_obs;
+    for (int g = 0; g < h->n_graphs; ++g)  // cached graphs hold the old pointer in their kernel parameters
+        if (h->graphs[g].exec) cudaGraphExecDestroy(h->graphs[g].exec);
+    h->n_graphs = 0;
+    h->graph_misses = 0;
+    memset(h->graphs, 0, sizeof(h->graphs));
+    return SG_OK;
+}
+
 // -DSG_CHECK_QUEUES builds: the device-side invariant counters of the split step's work queues (DevCfg::chk_err),
 // out[0..5] = violations by kind, out[6] = env steps checked.  Other builds: SG_ERR_INVALID ("not compiled in").
 extern "C" int sg_debug_queue_check(sg_env* h, uint64_t out[8]) {
@@ -2370,6 +2406,11 @@ static void launch_typed(const sg_env* h, const LaunchArgs& a) {
         const sg_env::Sub& sb = h->sub[a.sub];
         DevCfg dv = sb.dev;  // kernel parameter of this launch
         dv.pack_flags = a.pack_flags;
+        // terminal rows have the handle's observation dtype: device-path calls only (the host result block brings its
+        // own dtype and packed flags)
+        const bool term_ok = h->term_obs && a.obs && h->tail_mode != 1 && !a.pack_flags &&
+                             (a.obs_f32 != 0) == (h->cfg.obs_dtype == SG_OBS_F32);
+        dv.term_obs = term_ok ? (void*)((char*)h->term_obs + (size_t)sb.off * TR::D * sizeof(OT)) : nullptr;
         const long long off = sb.off;
         const int sms = h->sm_count > 0 ? h->sm_count : 148;
         const int hot_blocks = (int)((sb.n + kBlock - 1) / kBlock);
@@ -2628,7 +2669,6 @@ static int launch_split_step(sg_env* h, cudaStream_t user, const LaunchArgs& a, 
     return SG_OK;
 }
 
-static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 extern "C" int sg_reset(sg_env* h, const uint8_t* d_mask, void* d_obs, void* stream) {
     if (!h) return SG_ERR_INVALID;

@@ -105,6 +105,7 @@ class BatchedSpaceEnv:
         self._h = h
         self._host = None
         self._host_want_obs = True
+        self._term = None
         self._flip = 0
         self._init_spaces()
 
@@ -164,6 +165,20 @@ class BatchedSpaceEnv:
         check(self._L.sg_reset(self._h, self._ptr(mask), self._ptr(obs), self._stream()), self._h)
         return obs
 
+    def enable_terminal_observation(self, enable=True):
+        """Under auto-reset `step` returns the reset observation of an env that finished (gym 0.21 SyncVectorEnv); the
+        reference's own loop sees the episode's last observation because the caller resets (spaceship_env.py:68-78).
+        After this call the device-path `step` / `step_many` put that row into `info["terminal_observation"]`
+        ([N, D], the observation dtype; only rows of envs whose `done` is set in the step are new — the tensor is
+        persistent and the other rows keep what they held)."""
+        if enable:
+            self._term = torch.zeros((self.num_envs, self.obs_dim), dtype=self.obs_dtype, device=self.device)
+            check(self._L.sg_set_terminal_obs(self._h, self._ptr(self._term)), self._h)
+        else:
+            check(self._L.sg_set_terminal_obs(self._h, None), self._h)
+            self._term = None
+        return self._term
+
     def _assert_actions(self, a, is_torch):
         """action_space.contains for the whole batch (spaceship_env.py:69-72): Box(-1, 1, (2,)) or Discrete(6)."""
         if self.cfg.discrete:
@@ -182,7 +197,10 @@ class BatchedSpaceEnv:
             return self._step_host(actions, check_actions)
         obs, rew, done, info = self.step_many(actions[None] if actions.dim() == 2 else actions.view(1, -1, 2),
                                               check_actions)
-        return obs, rew[0], done[0], {"TimeLimit.truncated": info["TimeLimit.truncated"][0]}
+        out = {"TimeLimit.truncated": info["TimeLimit.truncated"][0]}
+        if "terminal_observation" in info:
+            out["terminal_observation"] = info["terminal_observation"]
+        return obs, rew[0], done[0], out
 
     def step_many(self, actions=None, check_actions=None, K=None, want_obs=True):
         """K env steps per call (split kernels, or one fused launch with step_mode="fused"). actions: f32 [K, N, 2]
@@ -216,7 +234,10 @@ class BatchedSpaceEnv:
         if self.copy:
             obs = obs.clone() if obs is not None else None
             rew, done, trunc = rew.clone(), done.clone(), trunc.clone()
-        return obs, rew, done, {"TimeLimit.truncated": trunc}
+        info = {"TimeLimit.truncated": trunc}
+        if self._term is not None and want_obs:
+            info["terminal_observation"] = self._term.clone() if self.copy else self._term
+        return obs, rew, done, info
 
     def rollout_random(self, K):
         """K env steps with the engine's synthetic uniform actions; nothing but statistics comes back."""

@@ -271,3 +271,42 @@ def test_masked_reset_of_a_live_batch_matches_the_oracle(oracle, case, env_id):
     o_d, r_d, d_d, _ = env.step(to_dev(a[0]))
     assert close(o_d.cpu().numpy(), o_o).all() and close(r_d.cpu().numpy(), r_o[0]).all()
     env.close()
+
+
+@pytest.mark.parametrize("case,env_id", [("goal3p", "GoalContinuous3P-v0"), ("kepler_circle", "KeplerCircleOrbit-v0"),
+                                          ("goal3p_discrete", None)])
+def test_terminal_observation_under_auto_reset(oracle, case, env_id):
+    """sg_set_terminal_obs / info["terminal_observation"]: for every env that restarts in a step (terminal event or
+    TimeLimit) the observation of the state its episode ended in — what the reference's loop sees with done = True
+    (spaceship_env.py:68-78) — against the oracle twin; rows of envs that did not finish keep their old content."""
+    from helpers import engine_kwargs
+    n, seed = 3000, 6
+    cfg = oracle_cfg(oracle, case, max_episode_steps=25)
+    eng = oracle.Engine(cfg, n, seed=seed)
+    eid, kw = engine_kwargs(case)
+    env = sg.make(eid, n, seed=seed, max_episode_steps=25, **kw)
+    term_d = env.enable_terminal_observation()
+    term_o = np.zeros((n, env.obs_dim))
+    assert close(env.reset().cpu().numpy(), eng.reset()).all()
+    rng = np.random.RandomState(12)
+    by_event = by_limit = 0
+    for t in range(60):
+        a = random_actions(rng, 1, n, bool(cfg.discrete))
+        o_o, r_o, d_o, tr_o = eng.step(a, term_obs=term_o)
+        o_d, r_d, d_d, info = env.step(to_dev(a[0]))
+        d = d_d.cpu().numpy()
+        assert (d == d_o[0].astype(bool)).all() and close(o_d.cpu().numpy(), o_o).all()
+        t_d = info["terminal_observation"].cpu().numpy()
+        assert close(t_d, term_o).all(), f"step {t}: terminal observation rows differ"
+        tr = info["TimeLimit.truncated"].cpu().numpy()
+        by_limit += int(tr.sum())
+        by_event += int((d & ~tr).sum())
+        # a finished env's terminal row is NOT the (reset) observation returned by the step
+        if d.any():
+            assert (np.abs(t_d[d] - o_d.cpu().numpy()[d]).max(axis=1) > 0).all()
+    assert by_event >= 1 and by_limit > 1000  # both kinds of endings were seen (Kepler orbits rarely crash in 25 steps)
+    assert info["terminal_observation"].data_ptr() != term_d.data_ptr()  # copy=True hands out a fresh tensor
+    env.enable_terminal_observation(False)
+    _, _, _, info = env.step(to_dev(random_actions(rng, 1, n, bool(cfg.discrete))[0]))
+    assert "terminal_observation" not in info
+    env.close()
