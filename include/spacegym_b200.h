@@ -200,7 +200,8 @@ int sg_reseed(sg_env* env, uint64_t seed);
  * observation instead (gym 0.21 SyncVectorEnv).  d_term_obs: [N][D] rows of the dtype of the step's d_obs (16-byte
  * aligned), or NULL to turn it off.  Every sg_step call that writes an observation (K = 1, or the last of K steps) then
  * also writes, for each env that restarted in that step, the observation of the state its episode ended in (terminal event or
- * TimeLimit); rows of other envs are not touched.  Synchronises the device. */
+ * TimeLimit); rows of other envs are not touched.  Split step path (the default) with device output buffers of the
+ * handle's obs_dtype; the K-fused kernel and the host result block do not produce it.  Synchronises the device. */
 int sg_set_terminal_obs(sg_env* env, void* d_term_obs);
 int64_t sg_kernel_launches(const sg_env* env);       /* kernels launched by this handle */
 /* Measurement aid, active when the handle was created with SG_TIMING=1 in the environment (sg_step then
